@@ -1,0 +1,109 @@
+"""ctypes binding of libstitchb200.so (the C ABI declared in include/stitch_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is
+missing it is built with nvcc; if that is impossible, or a kernel is asked to
+run on something that is not a B200, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint, c_void_p
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "libstitchb200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/stitch_b200.h one to one
+_P = c_void_p
+SIGNATURES = {
+    "sb_version": (c_int, []),
+    "sb_last_error": (c_char_p, []),
+    "sb_device_check": (c_int, []),
+    "sb_launch_count": (c_longlong, []),
+    "sb_reset_launch_count": (None, []),
+    "sb_debug_word": (c_uint, []),
+    "sb_corr_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "sb_corr": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sb_feat_to_tokens_bf16": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "sb_corr_tokens": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sb_avg_pool2x2": (c_int, [_P, _P, c_longlong, c_int, c_int, _P]),
+    "sb_corr_lookup": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, _P]),
+    "sb_bilinear_sampler": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sb_flow_warp": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "sb_homo_warp": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sb_tps_warp": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sb_range_map": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "sb_morph_open": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sb_composite_test_out": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "sb_build_model": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "sb_tps_mix_blend": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "sb_overlap_mask": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+}
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load (building first if needed) libstitchb200.so and declare every symbol."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise RuntimeError(f"{LIB_PATH} is missing (run __graft_entry__.build())")
+            from .build import build
+
+            build()
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def last_error() -> str:
+    msg = load().sb_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def stream_ptr() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t: torch.Tensor | None) -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    """The kernels take dense fp32 CUDA tensors; anything else is an error for
+    the device (no CPU path exists) and a cheap normalisation for layout/dtype."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name}: tensor is on {t.device}; stitch_b200 runs on B200 GPUs only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def launch_count() -> int:
+    return int(load().sb_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().sb_reset_launch_count()

@@ -1,0 +1,61 @@
+// abi.cu — library-wide state of libstitchb200: error string, device check,
+// launch counter.  No kernels here.
+#include <atomic>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_device() {
+  // Cached per device ordinal; a process drives one GPU (one process per GPU).
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_rc = SB_OK;
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDevice failed: %s (no CUDA device? this library has no CPU fallback)",
+              cudaGetErrorString(e));
+    return SB_ECUDA;
+  }
+  if (dev == cached_dev) {
+    if (cached_rc != SB_OK) set_error("device %d is not sm_100 (B200)", dev);
+    return cached_rc;
+  }
+  int major = 0, minor = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+    return SB_ECUDA;
+  }
+  cached_dev = dev;
+  cached_rc = (major == 10) ? SB_OK : SB_EARCH;
+  if (cached_rc != SB_OK)
+    set_error("device %d is sm_%d%d; libstitchb200 only runs on sm_100 (B200)", dev, major, minor);
+  return cached_rc;
+}
+
+}  // namespace sb
+
+extern "C" {
+
+int sb_version(void) { return SB_VERSION; }
+const char* sb_last_error(void) { return sb::g_err; }
+int sb_device_check(void) { return sb::check_device(); }
+long long sb_launch_count(void) { return sb::g_launches.load(std::memory_order_relaxed); }
+void sb_reset_launch_count(void) { sb::g_launches.store(0, std::memory_order_relaxed); }
+
+}  // extern "C"

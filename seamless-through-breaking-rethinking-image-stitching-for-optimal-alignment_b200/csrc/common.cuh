@@ -1,0 +1,104 @@
+// common.cuh — shared host/device helpers for libstitchb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/stitch_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libstitchb200 is written for sm_100a (B200) only"
+#endif
+
+namespace sb {
+
+// ----------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+int check_device();          // SB_OK if the current device is sm_100
+void count_launch(int n = 1);
+
+#define SB_REQUIRE(cond, code, ...)                 \
+  do {                                              \
+    if (!(cond)) {                                  \
+      sb::set_error(__VA_ARGS__);                   \
+      return (code);                                \
+    }                                               \
+  } while (0)
+
+#define SB_CUDA(expr)                                                        \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) {                                                 \
+      sb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                    __FILE__, __LINE__);                                     \
+      return SB_ECUDA;                                                       \
+    }                                                                        \
+  } while (0)
+
+// Checks the launch that was just enqueued (no sync).
+#define SB_LAUNCH_CHECK(name)                                                   \
+  do {                                                                          \
+    cudaError_t _e = cudaGetLastError();                                        \
+    if (_e != cudaSuccess) {                                                    \
+      sb::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));   \
+      return SB_ECUDA;                                                          \
+    }                                                                           \
+    sb::count_launch();                                                         \
+  } while (0)
+
+#define SB_ENTER()                         \
+  do {                                     \
+    int _rc = sb::check_device();          \
+    if (_rc != SB_OK) return _rc;          \
+  } while (0)
+
+inline cudaStream_t as_stream(sb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// --------------------------------------------------- exact fp32 arithmetic
+// The library is compiled with -fmad=false; these wrappers make the intended
+// rounding explicit where parity with the reference's separate ATen ops
+// (one rounding per op) matters.
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// Streaming (read-once) global loads / stores.
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// grid_sample(align_corners=True) coordinate round trip, as the reference's
+// Python + ATen's vectorised CPU kernel evaluate it (one rounding per op):
+//   g  = 2*v / max(size-1,1) - 1        (core/warp_utils.py:74-75, core/utils/utils.py:66-67)
+//   ix = (g + 1) * ((size-1)/2)         (ATen GridSamplerKernel.cpp ComputeLocation, align_corners)
+// `den` = max(size-1,1) as float, `half` = (size-1)/2 as float.
+__device__ __forceinline__ float grid_roundtrip(float v, float den, float half) {
+  float g = fsub(fdiv(fmul(2.0f, v), den), 1.0f);
+  return fmul(fadd(g, 1.0f), half);
+}
+
+}  // namespace sb

@@ -1,0 +1,565 @@
+// corr_tcgen05.cu — C1 (+ fused C2): FlowFormer's all-pairs cost volume.
+// Replaces MemoryEncoder.corr (core/FlowFormer/PerCostFormer3/encoder.py:359-369):
+//   corr[b, i, j] = sum_d fmap1[b, d, i] * fmap2[b, d, j]       heads = 1, no scale
+// and builds the avg-pool pyramid over the target axes (C2; F.avg_pool2d(.,2,2)
+// chained, the RAFT form hinted at encoder.py:376) in the GEMM epilogue.
+//
+// Two kernels:
+//  (1) feat_to_tokens_bf16: fp32 NCHW [B, C, N] -> bf16 token-major [B, N, Cpad]
+//      (K-major operands for the MMA; 12 B/element pre-pass, reusable for the
+//      forward and the backward volume of a pair).
+//  (2) corr_umma_kernel: persistent, warp-specialised tcgen05 GEMM, one CTA per
+//      SM.  Work unit = (batch b, 128-query block, group of 4 consecutive
+//      128-column target tiles):
+//        warp 0  TMA producer : A (128 x Cpad, resident for the unit) and a
+//                               2-stage ring of B tiles (128 x Cpad), SWIZZLE_128B
+//        warp 1  MMA issuer   : tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16,
+//                               fp32 accumulators in TMEM, 4 x 128-column buffers
+//        warp 2  TMEM alloc / dealloc (512 columns)
+//        warps 4-7 epilogue   : tcgen05.ld 32x32b.x32 -> registers -> (2x2 / 4x4 /
+//                               8x8 pooling in registers) -> swizzled smem -> TMA store
+//      K = C <= 256 is only 16 MMA k-steps per tile, so the kernel is bounded by
+//      the fp32 volume WRITE (64 KB per tile): roofline = HBM, not tensor pipe
+//      (SURVEY.md D4).  TMA stores write full 128-byte lines.
+//
+// With W2 == 64 a 128-column tile is exactly two target rows, so each epilogue
+// thread (one query row) holds everything the 2x2 pool needs; four consecutive
+// tiles give the 4x4 and 8x8 levels.
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched at run time)
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------- pre-pass
+constexpr int kTokTile = 64;
+
+__global__ void __launch_bounds__(256)
+feat_to_tokens_bf16_kernel(const float* __restrict__ fmap, uint16_t* __restrict__ tok, int C,
+                           int Cpad, int N) {
+  // tile: 64 channels x 64 tokens
+  __shared__ float s[kTokTile][kTokTile + 1];  // [token][channel]
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * kTokTile, n0 = blockIdx.x * kTokTile;
+  const float* src = fmap + (long long)b * C * N;
+  const bool vec = ((N & 3) == 0);
+  // load: 64 rows (channels) x 16 float4 (tokens)
+  for (int t = threadIdx.x; t < kTokTile * (kTokTile / 4); t += blockDim.x) {
+    const int cr = t / (kTokTile / 4), nq = (t % (kTokTile / 4)) * 4;
+    const int c = c0 + cr, n = n0 + nq;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+      const float* p = src + (long long)c * N + n;
+      if (vec && n + 3 < N) v = ldg_stream4(p);
+      else {
+        if (n < N) v.x = p[0];
+        if (n + 1 < N) v.y = p[1];
+        if (n + 2 < N) v.z = p[2];
+        if (n + 3 < N) v.w = p[3];
+      }
+    }
+    s[nq + 0][cr] = v.x; s[nq + 1][cr] = v.y; s[nq + 2][cr] = v.z; s[nq + 3][cr] = v.w;
+  }
+  __syncthreads();
+  // store: 64 tokens x 8 chunks of 8 channels (16 bytes of bf16)
+  uint16_t* dst = tok + (long long)b * N * Cpad;
+  for (int t = threadIdx.x; t < kTokTile * 8; t += blockDim.x) {
+    const int tr = t >> 3, ch = (t & 7) * 8;
+    const int n = n0 + tr;
+    if (n >= N) continue;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // round-to-nearest-even fp32 -> bf16 (pad channels are zeros already)
+      __nv_bfloat162 h = __floats2bfloat162_rn(s[tr][ch + 2 * k], s[tr][ch + 2 * k + 1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(dst + (long long)n * Cpad + c0 + ch) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ------------------------------------------------------------- GEMM kernel
+constexpr int BM = 128, BN = 128, BKP = 64;       // tile, K panel (64 bf16 = 128 B)
+constexpr int kMaxPanels = 4;                      // C <= 256
+constexpr int kPanelBytes = BM * 128;              // 16 KB
+constexpr int kStages = 2;
+constexpr int kTilesPerUnit = 4;
+constexpr int kAccBufs = 4;                        // 4 x 128 TMEM columns
+constexpr int kTmemCols = 512;
+constexpr int kStageBufBytes = 32 * 128;           // per-warp staging: 32 rows x 32 fp32
+constexpr int kSmemA = kMaxPanels * kPanelBytes;                 // 65536
+constexpr int kSmemB = kStages * kMaxPanels * kPanelBytes;       // 131072
+constexpr int kSmemStage = 4 * 2 * kStageBufBytes;               // 32768
+constexpr int kSmemBar = 256;
+constexpr int kSmemTotal = kSmemA + kSmemB + kSmemStage + kSmemBar + 1024;  // + align slack
+
+struct CorrParams {
+  int B, N1, N2, KP;            // KP = Cpad / 64
+  int MB, NT, NG;               // query blocks, target tiles, tile groups per (b, mblk)
+  long long n_units;
+  int H2h, H2q, H2e;            // H2/2, H2/4, H2/8 (pooling)
+  float* lvl1; float* lvl2; float* lvl3;
+  unsigned int* dbg;
+};
+
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);
+
+template <bool POOL>
+__global__ void __launch_bounds__(256, 1)
+corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_v, const CorrParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + kSmemA;
+  const uint32_t sStage = sB + kSmemB;
+  const uint32_t sBar = sStage + kSmemStage;
+  // barrier map (8 B each)
+  const uint32_t bar_a_full = sBar + 0, bar_a_empty = sBar + 8;
+  const uint32_t bar_b_full = sBar + 16;    // [kStages]
+  const uint32_t bar_b_empty = sBar + 32;   // [kStages]
+  const uint32_t bar_t_full = sBar + 48;    // [kAccBufs]
+  const uint32_t bar_t_empty = sBar + 80;   // [kAccBufs]
+  const uint32_t tmem_slot = sBar + 112;    // u32
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemA + kSmemB + kSmemStage + 112);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_b);
+    ptx::prefetch_tensormap(&map_v);
+  }
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(bar_a_full, 1);
+    ptx::mbar_init(bar_a_empty, 1);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(bar_b_full + 8 * s, 1);
+      ptx::mbar_init(bar_b_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < kAccBufs; ++a) {
+      ptx::mbar_init(bar_t_full + 8 * a, 1);
+      ptx::mbar_init(bar_t_empty + 8 * a, 4);   // one elected lane per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const uint32_t panel_tx = (uint32_t)p.KP * kPanelBytes;
+
+  if (warp == 0) {
+    // ================================================================ producer
+    if (lane == 0) {
+      uint32_t a_par = 0, stage = 0, b_par = 0;
+      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int ng = (int)(u % p.NG);
+        const long long r1 = u / p.NG;
+        const int mb = (int)(r1 % p.MB);
+        const int b = (int)(r1 / p.MB);
+        ptx::mbar_wait(bar_a_empty, a_par ^ 1, 1, p.dbg);
+        ptx::mbar_arrive_expect_tx(bar_a_full, panel_tx);
+        for (int kp = 0; kp < p.KP; ++kp)
+          ptx::tma_load_3d(sA + kp * kPanelBytes, &map_a, bar_a_full, kp * BKP, mb * BM, b);
+        a_par ^= 1;
+        const int t0 = ng * kTilesPerUnit;
+        const int t1 = min(t0 + kTilesPerUnit, p.NT);
+        for (int t = t0; t < t1; ++t) {
+          ptx::mbar_wait(bar_b_empty + 8 * stage, b_par ^ 1, 2, p.dbg);
+          ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, panel_tx);
+          for (int kp = 0; kp < p.KP; ++kp)
+            ptx::tma_load_3d(sB + (stage * kMaxPanels + kp) * kPanelBytes, &map_b,
+                             bar_b_full + 8 * stage, kp * BKP, t * BN, b);
+          if (++stage == kStages) { stage = 0; b_par ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t a_par = 0, stage = 0, b_par = 0, acc = 0, acc_par = 0;
+      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int ng = (int)(u % p.NG);
+        const int t0 = ng * kTilesPerUnit;
+        const int t1 = min(t0 + kTilesPerUnit, p.NT);
+        ptx::mbar_wait(bar_a_full, a_par, 3, p.dbg);
+        a_par ^= 1;
+        for (int t = t0; t < t1; ++t) {
+          ptx::mbar_wait(bar_t_empty + 8 * acc, acc_par ^ 1, 4, p.dbg);
+          ptx::mbar_wait(bar_b_full + 8 * stage, b_par, 5, p.dbg);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kp = 0; kp < p.KP; ++kp) {
+            const uint64_t adesc = ptx::umma_desc_k_sw128(sA + kp * kPanelBytes);
+            const uint64_t bdesc =
+                ptx::umma_desc_k_sw128(sB + (stage * kMaxPanels + kp) * kPanelBytes);
+#pragma unroll
+            for (int k = 0; k < BKP / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
+              ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kp | k) != 0);
+            }
+          }
+          ptx::umma_commit(bar_b_empty + 8 * stage);   // B stage reusable once these MMAs retire
+          ptx::umma_commit(bar_t_full + 8 * acc);      // accumulator ready for the epilogue
+          if (++stage == kStages) { stage = 0; b_par ^= 1; }
+          if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
+        }
+        ptx::umma_commit(bar_a_empty);                  // A reusable once the unit's MMAs retire
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================================================ epilogue
+    const int wq = warp - 4;                       // TMEM lane quarter == warp % 4
+    const uint32_t my_stage = sStage + wq * 2 * kStageBufBytes;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    uint32_t acc = 0, acc_par = 0, sbuf = 0;
+    // pooling state (one query row per thread)
+    float h1[32];   // level-1 partial sums of the current tile (target row pair)
+    float h2[16];   // level-2 partial sums across tile pairs
+    float h3[8];    // level-3 partial sums across the unit
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int ng = (int)(u % p.NG);
+      const long long r1 = u / p.NG;
+      const int mb = (int)(r1 % p.MB);
+      const int b = (int)(r1 / p.MB);
+      const int t0 = ng * kTilesPerUnit;
+      const int t1 = min(t0 + kTilesPerUnit, p.NT);
+      const int row = mb * BM + wq * 32 + lane;    // query index within the batch
+      const bool row_ok = row < p.N1;
+      const long long q = (long long)b * p.N1 + row;
+#pragma unroll
+      for (int tt = 0; tt < kTilesPerUnit; ++tt) {
+        const int t = t0 + tt;
+        if (t >= t1) break;
+        ptx::mbar_wait(bar_t_full + 8 * acc, acc_par, 6, p.dbg);
+        ptx::tc_fence_after_sync();
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_taddr + acc * BN + sl * 32, r);
+          ptx::tmem_ld_wait();
+          if (POOL) {
+            // W2 == 64: slices 0,1 = target row 2t (w 0..31, 32..63); 2,3 = row 2t+1.
+            // avg_pool2d order: ((a00 + a01) + a10) + a11, then * 0.25
+            const int hb = (sl & 1) * 16;
+            if (sl < 2) {
+#pragma unroll
+              for (int w = 0; w < 16; ++w)
+                h1[hb + w] = fadd(__uint_as_float(r[2 * w]), __uint_as_float(r[2 * w + 1]));
+            } else {
+#pragma unroll
+              for (int w = 0; w < 16; ++w)
+                h1[hb + w] = fmul(fadd(fadd(h1[hb + w], __uint_as_float(r[2 * w])),
+                                       __uint_as_float(r[2 * w + 1])), 0.25f);
+            }
+          }
+          // staging buffer `sbuf` was last read by the store issued two slices ago
+          if (lane == 0) ptx::tma_store_wait_read<1>();
+          __syncwarp();
+          const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t a = dst + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(r[4 * c]),
+                         "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3])
+                         : "memory");
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_3d(&map_v, my_stage + sbuf * kStageBufBytes, t * BN + sl * 32,
+                              mb * BM + wq * 32, b);
+            ptx::tma_store_commit();
+          }
+          sbuf ^= 1;
+        }
+        // accumulator buffer drained
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_t_empty + 8 * acc);
+        if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
+
+        if (POOL) {
+          if (p.lvl1 && row_ok) {
+            float* o = p.lvl1 + (q * p.H2h + t) * 32;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              stg_stream4(o + 4 * c, make_float4(h1[4 * c], h1[4 * c + 1], h1[4 * c + 2], h1[4 * c + 3]));
+          }
+          // level 2: pool level-1 rows (t even, t odd)
+          if ((tt & 1) == 0) {
+#pragma unroll
+            for (int w = 0; w < 16; ++w) h2[w] = fadd(h1[2 * w], h1[2 * w + 1]);
+          } else {
+#pragma unroll
+            for (int w = 0; w < 16; ++w)
+              h2[w] = fmul(fadd(fadd(h2[w], h1[2 * w]), h1[2 * w + 1]), 0.25f);
+            if (p.lvl2 && row_ok) {
+              float* o = p.lvl2 + (q * p.H2q + (t >> 1)) * 16;
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                stg_stream4(o + 4 * c, make_float4(h2[4 * c], h2[4 * c + 1], h2[4 * c + 2], h2[4 * c + 3]));
+            }
+            if (tt == 1) {
+#pragma unroll
+              for (int w = 0; w < 8; ++w) h3[w] = fadd(h2[2 * w], h2[2 * w + 1]);
+            } else {  // tt == 3
+#pragma unroll
+              for (int w = 0; w < 8; ++w)
+                h3[w] = fmul(fadd(fadd(h3[w], h2[2 * w]), h2[2 * w + 1]), 0.25f);
+              if (p.lvl3 && row_ok) {
+                float* o = p.lvl3 + (q * p.H2e + (t >> 2)) * 8;
+                stg_stream4(o, make_float4(h3[0], h3[1], h3[2], h3[3]));
+                stg_stream4(o + 4, make_float4(h3[4], h3[5], h3[6], h3[7]));
+              }
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------- standalone pooling
+__global__ void __launch_bounds__(256)
+avg_pool2x2_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int Ho,
+                   int Wo, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pl = i / ((long long)Ho * Wo);
+    const int rem = (int)(i - pl * Ho * Wo);
+    const int y = rem / Wo, x = rem - y * Wo;
+    const float* s = in + pl * H * W + (long long)(2 * y) * W + 2 * x;
+    const float2 a = *reinterpret_cast<const float2*>(s);
+    const float2 c = *reinterpret_cast<const float2*>(s + W);
+    out[i] = fmul(fadd(fadd(fadd(a.x, a.y), c.x), c.y), 0.25f);
+  }
+}
+
+// --------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+static int make_map_3d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base,
+                       unsigned long long d0, unsigned long long d1, unsigned long long d2,
+                       unsigned b0, unsigned b1, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return SB_ECUDA;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * (unsigned long long)elt_bytes, d0 * d1 * (unsigned long long)elt_bytes};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu x %llu x %llu)", what,
+              (int)r, d0, d1, d2);
+    return SB_ECUDA;
+  }
+  return SB_OK;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Word written (system scope) just before a protocol-timeout trap. It lives in
+// mapped pinned host memory so the host can still read it after the context died.
+static unsigned int* g_dbg_host = nullptr;
+static unsigned int* g_dbg = nullptr;
+
+}  // namespace sb
+
+extern "C" unsigned int sb_debug_word(void) { return sb::g_dbg_host ? *sb::g_dbg_host : 0u; }
+
+extern "C" size_t sb_corr_workspace_bytes(int B, int C, int N1, int N2) {
+  if (B < 0 || C < 0 || N1 < 0 || N2 < 0) return 0;
+  const size_t cpad = (size_t)sb::round_up(C, 64);
+  // 256-byte aligned halves
+  const size_t a = ((size_t)B * N1 * cpad * 2 + 255) / 256 * 256;
+  const size_t b = ((size_t)B * N2 * cpad * 2 + 255) / 256 * 256;
+  return a + b;
+}
+
+extern "C" int sb_feat_to_tokens_bf16(const float* fmap, void* tok, int B, int C, int N,
+                                      sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(fmap && tok, SB_EINVAL, "sb_feat_to_tokens_bf16: null pointer");
+  SB_REQUIRE(B >= 0 && C > 0 && N >= 0, SB_EINVAL, "sb_feat_to_tokens_bf16: bad size");
+  SB_REQUIRE(aligned16(fmap) && aligned16(tok), SB_EINVAL,
+             "sb_feat_to_tokens_bf16: pointers must be 16-byte aligned");
+  SB_REQUIRE(B <= 65535, SB_EUNSUP, "sb_feat_to_tokens_bf16: B > 65535");
+  if (B == 0 || N == 0) return SB_OK;
+  const int Cpad = round_up(C, 64);
+  dim3 grid((N + kTokTile - 1) / kTokTile, Cpad / kTokTile, B);
+  feat_to_tokens_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      fmap, reinterpret_cast<uint16_t*>(tok), C, Cpad, N);
+  SB_LAUNCH_CHECK("feat_to_tokens_bf16_kernel");
+  return SB_OK;
+}
+
+extern "C" int sb_avg_pool2x2(const float* in, float* out, long long planes, int H, int W,
+                              sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(in && out, SB_EINVAL, "sb_avg_pool2x2: null pointer");
+  SB_REQUIRE(planes >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_avg_pool2x2: bad size");
+  SB_REQUIRE((W & 1) == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0, SB_EUNSUP,
+             "sb_avg_pool2x2: W must be even and `in` 8-byte aligned");
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = planes * Ho * Wo;
+  if (total == 0) return SB_OK;
+  long long blocks = (total + 255) / 256;
+  const long long max_blocks = (long long)kNumSMs * 8 * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  avg_pool2x2_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(in, out, H, W, Ho, Wo, total);
+  SB_LAUNCH_CHECK("avg_pool2x2_kernel");
+  return SB_OK;
+}
+
+extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, float* lvl1,
+                              float* lvl2, float* lvl3, int B, int C, int H1, int W1, int H2,
+                              int W2, sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(tok1 && tok2 && vol, SB_EINVAL, "sb_corr_tokens: null pointer");
+  SB_REQUIRE(B >= 0 && C > 0 && H1 >= 0 && W1 >= 0 && H2 >= 0 && W2 >= 0, SB_EINVAL,
+             "sb_corr_tokens: bad size");
+  SB_REQUIRE(C <= 64 * kMaxPanels, SB_EUNSUP, "sb_corr_tokens: C=%d > %d not supported", C,
+             64 * kMaxPanels);
+  const long long N1 = (long long)H1 * W1, N2 = (long long)H2 * W2;
+  SB_REQUIRE(N1 < (1 << 30) && N2 < (1 << 30), SB_EUNSUP, "sb_corr_tokens: too many tokens");
+  if (B == 0 || N1 == 0 || N2 == 0) return SB_OK;
+  SB_REQUIRE((N2 & 3) == 0, SB_EUNSUP, "sb_corr_tokens: H2*W2 must be a multiple of 4 (TMA row pitch)");
+  SB_REQUIRE(aligned16(tok1) && aligned16(tok2) && aligned16(vol), SB_EINVAL,
+             "sb_corr_tokens: pointers must be 16-byte aligned");
+  const bool want_pool = lvl1 || lvl2 || lvl3;
+  if (want_pool)
+    SB_REQUIRE((H2 % 8) == 0 && (W2 % 8) == 0, SB_EUNSUP,
+               "sb_corr_tokens: pyramid needs H2, W2 multiples of 8 (got %d x %d)", H2, W2);
+  const bool fused_pool = want_pool && W2 == 64;
+  cudaStream_t s = as_stream(stream);
+  const int Cpad = round_up(C, 64);
+
+  CUtensorMap map_a, map_b, map_v;
+  int rc;
+  rc = make_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok1, Cpad, N1, B, BKP, BM, "A");
+  if (rc) return rc;
+  rc = make_map_3d(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok2, Cpad, N2, B, BKP, BN, "B");
+  if (rc) return rc;
+  rc = make_map_3d(&map_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, vol, N2, N1, B, 32, 32, "V");
+  if (rc) return rc;
+
+  if (!g_dbg) {
+    SB_CUDA(cudaHostAlloc(&g_dbg_host, 64, cudaHostAllocMapped));
+    *g_dbg_host = 0;
+    SB_CUDA(cudaHostGetDevicePointer(&g_dbg, g_dbg_host, 0));
+  }
+
+  CorrParams p;
+  p.B = B; p.N1 = (int)N1; p.N2 = (int)N2; p.KP = Cpad / 64;
+  p.MB = (int)((N1 + BM - 1) / BM);
+  p.NT = (int)((N2 + BN - 1) / BN);
+  p.NG = (p.NT + kTilesPerUnit - 1) / kTilesPerUnit;
+  p.n_units = (long long)B * p.MB * p.NG;
+  p.H2h = H2 / 2; p.H2q = H2 / 4; p.H2e = H2 / 8;
+  p.lvl1 = fused_pool ? lvl1 : nullptr;
+  p.lvl2 = fused_pool ? lvl2 : nullptr;
+  p.lvl3 = fused_pool ? lvl3 : nullptr;
+  p.dbg = g_dbg;
+
+  const int grid = (int)((p.n_units < kNumSMs) ? p.n_units : kNumSMs);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    attr_set = true;
+  }
+  if (fused_pool)
+    corr_umma_kernel<true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, p);
+  else
+    corr_umma_kernel<false><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, p);
+  SB_LAUNCH_CHECK("corr_umma_kernel");
+
+  if (want_pool && !fused_pool) {
+    // generic target width: chained standalone pooling over the finished volume
+    const long long planes = (long long)B * N1;
+    float* l1 = lvl1;
+    SB_REQUIRE(lvl1 != nullptr, SB_EUNSUP,
+               "sb_corr_tokens: for W2 != 64 the pyramid is chained, lvl1 must be provided");
+    rc = sb_avg_pool2x2(vol, l1, planes, H2, W2, stream);
+    if (rc) return rc;
+    if (lvl2 || lvl3) {
+      SB_REQUIRE(lvl2 != nullptr, SB_EUNSUP, "sb_corr_tokens: lvl3 requires lvl2 when W2 != 64");
+      rc = sb_avg_pool2x2(l1, lvl2, planes, H2 / 2, W2 / 2, stream);
+      if (rc) return rc;
+    }
+    if (lvl3) {
+      rc = sb_avg_pool2x2(lvl2, lvl3, planes, H2 / 4, W2 / 4, stream);
+      if (rc) return rc;
+    }
+  }
+  return SB_OK;
+}
+
+extern "C" int sb_corr(const float* fmap1, const float* fmap2, float* vol, float* lvl1, float* lvl2,
+                       float* lvl3, void* workspace, size_t workspace_bytes, int B, int C, int H1,
+                       int W1, int H2, int W2, sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(fmap1 && fmap2 && vol, SB_EINVAL, "sb_corr: null pointer");
+  SB_REQUIRE(B >= 0 && C > 0 && H1 >= 0 && W1 >= 0 && H2 >= 0 && W2 >= 0, SB_EINVAL, "sb_corr: bad size");
+  const long long N1 = (long long)H1 * W1, N2 = (long long)H2 * W2;
+  if (B == 0 || N1 == 0 || N2 == 0) return SB_OK;
+  const size_t need = sb_corr_workspace_bytes(B, C, (int)N1, (int)N2);
+  SB_REQUIRE(workspace && workspace_bytes >= need, SB_EINVAL,
+             "sb_corr: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+  SB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, SB_EINVAL,
+             "sb_corr: workspace must be 256-byte aligned");
+  const size_t cpad = (size_t)round_up(C, 64);
+  const size_t a_bytes = ((size_t)B * N1 * cpad * 2 + 255) / 256 * 256;
+  void* tok1 = workspace;
+  void* tok2 = static_cast<uint8_t*>(workspace) + a_bytes;
+  int rc = sb_feat_to_tokens_bf16(fmap1, tok1, B, C, (int)N1, stream);
+  if (rc) return rc;
+  rc = sb_feat_to_tokens_bf16(fmap2, tok2, B, C, (int)N2, stream);
+  if (rc) return rc;
+  return sb_corr_tokens(tok1, tok2, vol, lvl1, lvl2, lvl3, B, C, H1, W1, H2, W2, stream);
+}

@@ -1,0 +1,102 @@
+// homo_warp.cu — W2: homography backward warp with the UDIS sampler.
+// Replaces transformer(U, theta, out_size) (core/udis_utils/torch_homo_transform.py:5-151):
+//   _meshgrid (:94-112)  -> (xs[c], ys[r], 1)          (linspace tables passed in)
+//   _transform (:114-145)-> T_g = theta @ grid; t += 1e-6 where |t| < 1e-7; x = X/t, y = Y/t
+//   _interpolate (:17-92)-> UdisTap (bilinear.cuh)
+//
+// The 3-term dot product is evaluated as the oracle's BLAS does for K = 3:
+//   acc = t0*gx ; acc = fma(t1, gy, acc) ; acc = fma(t2, 1, acc)
+// (verified bit-for-bit against torch.matmul on CPU, see tests/golden).
+//
+// HBM-bound: coordinates are computed, not loaded; per output pixel C planes
+// are gathered (4 taps) and C floats written: 2*C*4 algorithmic bytes / px.
+#include "bilinear.cuh"
+
+namespace sb {
+
+__device__ __forceinline__ float dot3(const float* t, float gx, float gy) {
+  float acc = fmul(t[0], gx);
+  acc = __fmaf_rn(t[1], gy, acc);
+  acc = __fmaf_rn(t[2], 1.0f, acc);
+  return acc;
+}
+
+template <int C_T>
+__global__ void __launch_bounds__(256)
+homo_warp_kernel(const float* __restrict__ U, const float* __restrict__ theta,
+                 const float* __restrict__ xs, const float* __restrict__ ys,
+                 float* __restrict__ out, int32_t* __restrict__ idx_dbg,
+                 int C_rt, int H, int W, int Hout, int Wout, int theta_batch,
+                 long long total /* B*Hout*Wout */) {
+  const int C = (C_T > 0) ? C_T : C_rt;
+  const long long oplane = (long long)Hout * Wout;
+  const long long iplane = (long long)H * W;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const long long b = p / oplane;
+    const long long rem = p - b * oplane;
+    const int r = (int)(rem / Wout), c = (int)(rem - (long long)r * Wout);
+    const float* th = theta + (theta_batch > 1 ? b * 9 : 0);
+    float t[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) t[i] = __ldg(th + i);
+    const float gx = __ldg(xs + c), gy = __ldg(ys + r);
+    const float X = dot3(t, gx, gy), Y = dot3(t + 3, gx, gy);
+    float T = dot3(t + 6, gx, gy);
+    // smallers = 1e-6 * (1 - float(|t| >= 1e-7)); t = t + smallers   (:133-137)
+    const float ge = (fabsf(T) >= 1e-7f) ? 1.0f : 0.0f;
+    T = fadd(T, fmul(1e-6f, fsub(1.0f, ge)));
+    UdisTap tap;
+    tap.setup(fdiv(X, T), fdiv(Y, T), H, W);
+    if (idx_dbg) {
+      int32_t* d = idx_dbg + b * 4 * oplane + rem;
+      d[0] = tap.x0; d[oplane] = tap.x1; d[2 * oplane] = tap.y0; d[3 * oplane] = tap.y1;
+    }
+    const float* src = U + b * C * iplane;
+    float* dst = out + b * C * oplane + rem;
+    if (C_T > 0) {
+      float v[C_T > 0 ? C_T : 1];
+#pragma unroll
+      for (int ch = 0; ch < C_T; ++ch) v[ch] = tap.sample(src + ch * iplane, W);
+#pragma unroll
+      for (int ch = 0; ch < C_T; ++ch) stg_stream(dst + ch * oplane, v[ch]);
+    } else {
+      for (int ch = 0; ch < C; ++ch) stg_stream(dst + ch * oplane, tap.sample(src + ch * iplane, W));
+    }
+  }
+}
+
+}  // namespace sb
+
+extern "C" int sb_homo_warp(const float* U, const float* theta, const float* xs, const float* ys,
+                            float* out, int32_t* idx_dbg, int B, int C, int H, int W, int Hout,
+                            int Wout, int theta_batch, sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(U && theta && xs && ys && out, SB_EINVAL, "sb_homo_warp: null pointer");
+  SB_REQUIRE(B >= 0 && C >= 0 && H > 0 && W > 0 && Hout >= 0 && Wout >= 0, SB_EINVAL,
+             "sb_homo_warp: bad size");
+  SB_REQUIRE(theta_batch == 1 || theta_batch == B, SB_EINVAL,
+             "sb_homo_warp: theta batch %d must be 1 or B=%d", theta_batch, B);
+  SB_REQUIRE((long long)H * W < (1ll << 31) && (long long)Hout * Wout < (1ll << 31), SB_EUNSUP,
+             "sb_homo_warp: plane too large");
+  const long long total = (long long)B * Hout * Wout;
+  if (total == 0 || C == 0) return SB_OK;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long max_blocks = (long long)kNumSMs * 8 * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  cudaStream_t s = as_stream(stream);
+#define SB_HOMO_LAUNCH(CT)                                                                    \
+  homo_warp_kernel<CT><<<(int)blocks, threads, 0, s>>>(U, theta, xs, ys, out, idx_dbg, C, H, \
+                                                       W, Hout, Wout, theta_batch, total)
+  switch (C) {
+    case 1: SB_HOMO_LAUNCH(1); break;
+    case 3: SB_HOMO_LAUNCH(3); break;
+    case 6: SB_HOMO_LAUNCH(6); break;
+    default: SB_HOMO_LAUNCH(0); break;
+  }
+#undef SB_HOMO_LAUNCH
+  SB_LAUNCH_CHECK("homo_warp_kernel");
+  return SB_OK;
+}

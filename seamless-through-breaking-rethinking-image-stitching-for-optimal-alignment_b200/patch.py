@@ -1,0 +1,42 @@
+"""patch_reference() — drop the B200 kernels in behind the reference's own call
+surface by assigning this package's functions over the reference modules'
+attributes (SURVEY §8b lists the call sites). The reference must already be
+importable (``sys.path`` containing its root and ``core/``)."""
+from __future__ import annotations
+
+import importlib
+
+__all__ = ["patch_reference"]
+
+
+def patch_reference(verbose: bool = False):
+    from . import composition, corr, lookup, torch_homo_transform, torch_tps_transform, warp_utils
+
+    done = []
+
+    def _set(modname, attr, fn, cls=None):
+        try:
+            mod = importlib.import_module(modname)
+        except Exception as e:  # the reference module itself may be un-importable (missing timm, ...)
+            if verbose:
+                print(f"[stitch_b200] skip {modname}.{attr}: {e}")
+            return
+        target = getattr(mod, cls) if cls else mod
+        setattr(target, attr, fn)
+        done.append(f"{modname}.{(cls + '.') if cls else ''}{attr}")
+
+    _set("core.warp_utils", "warp", warp_utils.warp)
+    _set("core.warp_utils", "compute_range_map", warp_utils.compute_range_map)
+    _set("core.warp_utils", "compute_occlusion", warp_utils.compute_occlusion)
+    _set("core.udis_utils.torch_homo_transform", "transformer", torch_homo_transform.transformer)
+    _set("core.udis_utils.torch_tps_transform", "transformer", torch_tps_transform.transformer)
+    _set("core.udis_utils.torch_tps_transform2", "transformer", torch_tps_transform.transformer)
+    _set("core.utils.utils", "bilinear_sampler", lookup.bilinear_sampler)
+    _set("core.UDIS2.Composition.network", "build_model", composition.build_model)
+    _set("core.flowHomoAdpater", "preprocess_occlusion_mask", composition.preprocess_occlusion_mask)
+    _set("core.flowHomoAdpater", "warp", warp_utils.warp)                 # star-imported name (:16)
+    _set("core.flowHomoAdpater", "compute_occlusion", warp_utils.compute_occlusion)
+    _set("core.FlowFormer.PerCostFormer3.encoder", "corr", corr.memory_encoder_corr, cls="MemoryEncoder")
+    _set("core.FlowFormer.PerCostFormer3.decoder", "encode_flow_token",
+         lookup.memory_decoder_encode_flow_token, cls="MemoryDecoder")
+    return done

@@ -1,0 +1,148 @@
+"""The hot path as one callable step, plus the pair sharding used for multi-GPU.
+
+One *step* = one batch of stitched pairs through the op list of the reference's
+``train_eval_foward`` (``core/flowHomoAdpater.py:83-191``) with the networks
+replaced by their synthetic outputs:
+
+    per pair: 2 x C1 (+C2)   cost volume forward / backward, pyramid in the epilogue
+              24 x C3        12 lookups per direction
+              2 x W2         homography warp of (img2|1) and (img1|1)
+              W4             'wang' occlusion from the two flows, thresholded
+              W1             flow warp of output_H (+ overlap, + occlusion multiply)
+
+Pairs are independent, so N GPUs simply take disjoint contiguous slices of the
+pair list (``shard_range``); the only collective is the final metric reduction.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import corr as corr_mod
+from . import lookup, torch_DLT, torch_homo_transform, warp_utils
+
+__all__ = ["shard_range", "PairBatch", "make_pair_batch", "HotPath", "algorithmic_work"]
+
+BASE_SEED = 1234  # out.py:7-8 of the reference seeds with 1234
+
+
+def shard_range(n_total: int, rank: int, world_size: int):
+    """Contiguous, balanced split of ``range(n_total)``: rank r gets [start, stop)."""
+    if world_size <= 0 or not 0 <= rank < world_size:
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    base, rem = divmod(n_total, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+@dataclass
+class PairBatch:
+    """Synthetic UDIS-D-shaped inputs of one batch of pairs (host or device)."""
+    image1: torch.Tensor    # [B,3,S,S] 0..255
+    image2: torch.Tensor
+    fmap1: torch.Tensor     # [B,256,S/8,S/8]  stand-in for the Twins features
+    fmap2: torch.Tensor
+    h_motion: torch.Tensor  # [B,4,2]          stand-in for the homography regressor
+    flow_ij: torch.Tensor   # [B,2,S,S]        stand-in for FlowFormer's output
+    flow_ji: torch.Tensor
+    coords: torch.Tensor    # [2*iters,B,2,S/8,S/8] lookup centres, one per GRU iteration and direction
+
+    def tensors(self):
+        return [self.image1, self.image2, self.fmap1, self.fmap2, self.h_motion, self.flow_ij,
+                self.flow_ji, self.coords]
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.tensors())
+
+    def map(self, fn):
+        return PairBatch(*[fn(t) for t in self.tensors()])
+
+
+def make_pair_batch(first_pair: int, batch: int, size: int = 512, iters: int = 12, channels: int = 256) -> PairBatch:
+    """CPU tensors for pairs [first_pair, first_pair+batch); pair p uses seed 1234 + p,
+    so any sharding of the pair list sees identical per-pair inputs."""
+    s8 = size // 8
+    per = []
+    for p in range(first_pair, first_pair + batch):
+        g = torch.Generator().manual_seed(BASE_SEED + p)
+        im1 = torch.rand(3, size, size, generator=g) * 255.0
+        im2 = torch.rand(3, size, size, generator=g) * 255.0
+        f1 = torch.randn(channels, s8, s8, generator=g)
+        f2 = torch.randn(channels, s8, s8, generator=g)
+        hm = torch.randn(4, 2, generator=g) * (20.0 * size / 512.0)
+        # smooth residual flows: N(0, 2^2) at 1/8 resolution, bilinearly upsampled x8
+        lo = torch.randn(2, 2, s8, s8, generator=g) * 2.0
+        up = torch.nn.functional.interpolate(lo, size=(size, size), mode="bilinear", align_corners=True)
+        grid = lookup.coords_grid(1, s8, s8)[0]
+        co = grid[None] + torch.randn(2 * iters, 2, s8, s8, generator=g) * 2.0
+        per.append((im1, im2, f1, f2, hm, up[0], up[1], co))
+    stack = [torch.stack([x[i] for x in per]) for i in range(8)]
+    stack[7] = stack[7].permute(1, 0, 2, 3, 4).contiguous()     # [2*iters, B, 2, h, w]
+    return PairBatch(*stack)
+
+
+def algorithmic_work(batch: int, size: int = 512, iters: int = 12, channels: int = 256, pyramid: bool = True):
+    """Algorithmic FLOPs and HBM bytes of one step (SURVEY §8(d) per-unit figures x units)."""
+    n = (size // 8) ** 2
+    px = size * size
+    vol_bytes = n * n * 4 + 2 * n * channels * 4
+    pyr_bytes = n * n * 4 * (1 / 4 + 1 / 16 + 1 / 64) if pyramid else 0.0
+    per_pair = {
+        "corr_flops": 2 * (2.0 * n * n * channels),
+        "corr_bytes": 2 * (vol_bytes + pyr_bytes),
+        "lookup_bytes": 2 * iters * n * 732.0,
+        "homo_bytes": 2 * px * 48.0,
+        "flow_warp_bytes": px * (56.0 + 4.0 + 4.0),     # + occlusion mask read + overlap write
+        "range_map_bytes": px * 28.0,
+    }
+    tot = {k: v * batch for k, v in per_pair.items()}
+    tot["bytes"] = sum(v for k, v in tot.items() if k.endswith("_bytes"))
+    tot["flops"] = tot["corr_flops"]
+    return tot
+
+
+class HotPath:
+    """Runs the step on the current CUDA device through the package's public,
+    reference-shaped functions (the same calls a patched reference makes)."""
+
+    def __init__(self, size: int = 512, iters: int = 12, pyramid: bool = True, r: int = 4):
+        self.size, self.iters, self.pyramid, self.r = size, iters, pyramid, r
+
+    def step(self, pb: PairBatch):
+        size, iters = self.size, self.iters
+        dev = pb.image1.device
+        b = pb.image1.shape[0]
+        # ---- cost volumes, forward and backward (MemoryEncoder.corr x 2)
+        lv = 3 if self.pyramid else 0
+        vol_f = corr_mod.corr(pb.fmap1, pb.fmap2, pyramid_levels=lv)
+        vol_b = corr_mod.corr(pb.fmap2, pb.fmap1, pyramid_levels=lv)
+        if self.pyramid:
+            (vol_f, pyr_f), (vol_b, pyr_b) = vol_f, vol_b
+        s8 = size // 8
+        maps_f = vol_f.view(b * s8 * s8, 1, s8, s8)      # encoder.py:260 (free view)
+        maps_b = vol_b.view(b * s8 * s8, 1, s8, s8)
+        # ---- 12 lookups per direction (MemoryDecoder.encode_flow_token)
+        tokens = []
+        for it in range(iters):
+            tokens.append(lookup.encode_flow_token(maps_f, pb.coords[it], self.r))
+        for it in range(iters):
+            tokens.append(lookup.encode_flow_token(maps_b, pb.coords[iters + it], self.r))
+        # ---- homography stage (flowHomoAdpater.py:92-113)
+        src_p = torch.tensor([[0.0, 0.0], [size, 0.0], [0.0, size], [size, size]], device=dev)
+        src_p = src_p.unsqueeze(0).expand(b, -1, -1)
+        H = torch_DLT.tensor_DLT(src_p / 8, (src_p + pb.h_motion) / 8)
+        M = torch.tensor([[size / 16.0, 0.0, size / 16.0], [0.0, size / 16.0, size / 16.0], [0.0, 0.0, 1.0]], device=dev)
+        M_inv = torch.inverse(M)
+        H_mat = M_inv @ H @ M
+        H_inv_mat = M_inv @ torch.inverse(H) @ M
+        ones = torch.ones_like(pb.image2)
+        output_H = torch_homo_transform.transformer(torch.cat((pb.image2, ones), 1), H_mat, (size, size))
+        output_H_inv = torch_homo_transform.transformer(torch.cat((pb.image1, ones), 1), H_inv_mat, (size, size))
+        # ---- occlusion + flow warp (+ overlap, + multiply) (:170-182)
+        occ = warp_utils.compute_occlusion(pb.flow_ij, pb.flow_ji, "wang", occlusion_are_zeros=True,
+                                           boundaries_occluded=True, threshold=True)
+        final_warp, overlap = warp_utils.warp(output_H, pb.flow_ij, mul_mask=occ, return_overlap=True)
+        return dict(final_warp_output=final_warp, overlap=overlap, origin_occlusion_mask=occ,
+                    output_H=output_H, output_H_inv=output_H_inv, cost_tokens=tokens,
+                    cost_volume=vol_f, cost_volume_back=vol_b)

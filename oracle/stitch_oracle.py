@@ -1,0 +1,287 @@
+"""numpy front-end of the CPU oracle (oracle.c) — TEST INFRASTRUCTURE ONLY.
+
+A CPU restatement of the reference's hot-path arithmetic used (a) by tests/ as
+the checker for the CUDA kernels, (b) by __graft_entry__.smoke(), and (c) by
+bench.py's cpu_baseline / --impl reference legs as the timed CPU port.  The
+product package (stitch_b200) never imports this module.
+
+Parity status: pinned — every function here is checked against golden vectors
+produced by running the reference's own Python functions
+(tests/golden/make_golden.py -> tests/golden/*.npz; tests/test_oracle_golden.py).
+Exceptions, which have no reference implementation to pin against:
+the avg-pool pyramid C2 and the pyramid lookup C3p ("parity unpinned by the
+reference": pinned only against torch's avg_pool2d / the reference's
+bilinear_sampler applied with the dead code's convention).
+
+All arrays are C-contiguous numpy float32 unless noted; names, argument meaning
+and output shapes follow the reference functions cited in oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_longlong, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_oracle_build", os.path.join(_HERE, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _lib = ctypes.CDLL(mod.build())
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return c_void_p(0) if a is None else c_void_p(a.ctypes.data)
+
+
+def linspace_table(n):
+    """torch.linspace(-1, 1, n) — taken from torch itself (the reference builds it with
+    torch on the CPU, torch_homo_transform.py:96-99; it is an INPUT of the kernels)."""
+    import torch
+    return torch.linspace(-1.0, 1.0, int(n)).numpy().copy()
+
+
+# ----------------------------------------------------------------- C1 / C2
+def corr(fmap1, fmap2, heads=1, use_blas=True):
+    """MemoryEncoder.corr (encoder.py:359-369): fp32 einsum 'bhid,bhjd->bhij'."""
+    f1, f2 = _f32(fmap1), _f32(fmap2)
+    b, dim, h1, w1 = f1.shape
+    _, _, h2, w2 = f2.shape
+    d = dim // heads
+    a = f1.reshape(b * heads, d, h1 * w1)
+    c = f2.reshape(b * heads, d, h2 * w2)
+    if use_blas:
+        vol = np.matmul(a.transpose(0, 2, 1), c)
+    else:
+        vol = np.empty((b * heads, h1 * w1, h2 * w2), np.float32)
+        _load().o_corr(_p(a), _p(c), _p(vol), c_int(b * heads), c_int(d), c_int(h1 * w1), c_int(h2 * w2))
+    return np.ascontiguousarray(vol, dtype=np.float32).reshape(b, heads, h1, w1, h2, w2)
+
+
+def corr_bf16_inputs(fmap1, fmap2):
+    """The same contraction on bf16-rounded operands accumulated in fp64: what the
+    tcgen05 kernel computes up to fp32 accumulation order (used to separate the
+    bf16 rounding contract from kernel bugs)."""
+    import torch
+    r1 = torch.from_numpy(_f32(fmap1)).bfloat16().double().numpy()
+    r2 = torch.from_numpy(_f32(fmap2)).bfloat16().double().numpy()
+    b, dim, h1, w1 = r1.shape
+    _, _, h2, w2 = r2.shape
+    vol = np.matmul(r1.reshape(b, dim, -1).transpose(0, 2, 1), r2.reshape(b, dim, -1))
+    return vol.reshape(b, 1, h1, w1, h2, w2)
+
+
+def avg_pool2x2(x):
+    """F.avg_pool2d(x, 2, stride=2) on [..., H, W]."""
+    x = _f32(x)
+    h, w = x.shape[-2:]
+    planes = int(np.prod(x.shape[:-2])) if x.ndim > 2 else 1
+    out = np.empty(x.shape[:-2] + (h // 2, w // 2), np.float32)
+    _load().o_avg_pool2x2(_p(x), _p(out), c_longlong(planes), c_int(h), c_int(w))
+    return out
+
+
+def corr_pyramid(fmap1, fmap2, num_levels=4):
+    vol = corr(fmap1, fmap2)
+    b, _, h1, w1, h2, w2 = vol.shape
+    lv = [vol.reshape(b * h1 * w1, 1, h2, w2)]
+    for _ in range(num_levels - 1):
+        lv.append(avg_pool2x2(lv[-1]))
+    return lv
+
+
+# ----------------------------------------------------------------- C3 / C3p
+def encode_flow_token(cost_maps, coords, r=4, coord_scale=1.0):
+    """decoder.py:242-260 -> logical [B,(2r+1)^2,H1,W1] (returned as that view of a
+    [B,H1,W1,(2r+1)^2] array, like the reference)."""
+    cm, co = _f32(cost_maps), _f32(coords)
+    b, _, h1, w1 = co.shape
+    nq, heads, h2, w2 = cm.shape
+    assert heads == 1 and nq == b * h1 * w1
+    k = (2 * r + 1) ** 2
+    out = np.empty((b, h1, w1, k), np.float32)
+    _load().o_corr_lookup(_p(cm), _p(co), _p(out), c_int(b), c_int(h1), c_int(w1), c_int(h2), c_int(w2),
+                          c_int(r), c_float(coord_scale), c_int(k), c_int(0))
+    return out.transpose(0, 3, 1, 2)
+
+
+def encode_flow_token_pyramid(pyramid, coords, r=4):
+    outs = [encode_flow_token(cm, coords, r, 1.0 / (1 << l)) for l, cm in enumerate(pyramid)]
+    return np.concatenate(outs, axis=1)
+
+
+def bilinear_sampler(img, coords):
+    im, co = _f32(img), _f32(coords)
+    n, c, h, w = im.shape
+    ho, wo = co.shape[1:3]
+    out = np.empty((n, c, ho, wo), np.float32)
+    _load().o_bilinear_sampler(_p(im), _p(co), _p(out), c_int(n), c_int(c), c_int(h), c_int(w), c_int(ho), c_int(wo))
+    return out
+
+
+# ----------------------------------------------------------------- W1
+def warp(x, flo, mul_mask=None, return_overlap=False):
+    x, flo = _f32(x), _f32(flo)
+    b, c, h, w = x.shape
+    mm = None if mul_mask is None else _f32(mul_mask)
+    out = np.empty_like(x)
+    ov = np.empty((b, h, w), np.float32) if return_overlap else None
+    _load().o_flow_warp(_p(x), _p(flo), _p(mm), _p(out), _p(ov), c_int(b), c_int(c), c_int(h), c_int(w))
+    return (out, ov) if return_overlap else out
+
+
+# ----------------------------------------------------------------- W2 / W3
+def homo_transformer(U, theta, out_size, return_indices=False):
+    U = _f32(U)
+    th = _f32(theta).reshape(-1, 3, 3)
+    b, c, h, w = U.shape
+    ho, wo = int(out_size[0]), int(out_size[1])
+    xs, ys = linspace_table(wo), linspace_table(ho)
+    out = np.empty((b, c, ho, wo), np.float32)
+    idx = np.empty((b, 4, ho, wo), np.int32) if return_indices else None
+    _load().o_homo_warp(_p(U), _p(th), _p(xs), _p(ys), _p(out), _p(idx), c_int(b), c_int(c), c_int(h), c_int(w),
+                        c_int(ho), c_int(wo), c_int(th.shape[0]))
+    return (out, idx) if return_indices else out
+
+
+def tps_solve_system(source, target):
+    """torch_tps_transform.py:149-185 in numpy (fp32 kernel matrix, fp64 inverse)."""
+    src = _f32(source)
+    tgt = _f32(target)
+    b, pn, _ = src.shape
+    ones = np.ones((b, pn, 1), np.float32)
+    p = np.concatenate([ones, src], 2)
+    diff = p.reshape(b, pn, 1, 3) - p.reshape(b, 1, pn, 3)
+    d2 = np.sum(np.square(diff), 3, dtype=np.float32)
+    r = d2 * np.log(d2 + np.float32(1e-6))
+    w0 = np.concatenate((p, r), 2)
+    w1 = np.concatenate((np.zeros((b, 3, 3), np.float32), p.transpose(0, 2, 1)), 2)
+    wmat = np.concatenate((w0, w1), 1).astype(np.float64)
+    w_inv = np.linalg.inv(wmat)
+    tp = np.concatenate((tgt, np.zeros((b, 3, 2), np.float32)), 1).astype(np.float64)
+    T = np.matmul(w_inv, tp).transpose(0, 2, 1)
+    return np.ascontiguousarray(T, dtype=np.float32)
+
+
+def tps_transformer(U, source, target, out_size, return_indices=False, return_coords=False, T=None):
+    U = _f32(U)
+    src = _f32(source)
+    b, c, h, w = U.shape
+    pn = src.shape[1]
+    T = tps_solve_system(source, target) if T is None else _f32(T)
+    ho, wo = int(out_size[0]), int(out_size[1])
+    xs, ys = linspace_table(wo), linspace_table(ho)
+    out = np.empty((b, c, ho, wo), np.float32)
+    idx = np.empty((b, 4, ho, wo), np.int32) if return_indices else None
+    crd = np.empty((b, 2, ho, wo), np.float32) if return_coords else None
+    _load().o_tps_warp(_p(U), _p(T), _p(src), _p(xs), _p(ys), _p(out), _p(idx), _p(crd), c_int(b), c_int(c),
+                       c_int(h), c_int(w), c_int(ho), c_int(wo), c_int(pn))
+    res = [out]
+    if return_indices:
+        res.append(idx)
+    if return_coords:
+        res.append(crd)
+    return res[0] if len(res) == 1 else tuple(res)
+
+
+# ----------------------------------------------------------------- W4 / W5
+def _range(flow, mode):
+    fl = _f32(flow)
+    b, _, h, w = fl.shape
+    out = np.empty((b, 1, h, w), np.float32)
+    _load().o_range_map(_p(fl), _p(out), c_int(b), c_int(h), c_int(w), c_int(mode))
+    return out
+
+
+def compute_range_map(flow):
+    return _range(flow, 0)
+
+
+def compute_occlusion_wang(flow_ji, occlusion_are_zeros=True, threshold=False):
+    if occlusion_are_zeros:
+        return _range(flow_ji, 3 if threshold else 1)
+    occ = _range(flow_ji, 2)
+    return (occ >= 0.5).astype(np.float32) if threshold else occ
+
+
+def morph_open(mask, kernel_size=(19, 19), border_is_zero=True):
+    m = _f32(mask)
+    h, w = m.shape[-2:]
+    planes = m.size // (h * w)
+    out = np.empty_like(m)
+    _load().o_morph_open(_p(m), _p(out), c_int(planes), c_int(h), c_int(w), c_int(kernel_size[0]),
+                         c_int(kernel_size[1]), c_int(1 if border_is_zero else 0))
+    return out
+
+
+def preprocess_occlusion_mask(mask, kernel_size=(19, 19)):
+    return morph_open(mask, kernel_size, True)
+
+
+# ----------------------------------------------------------------- W6 / W7 / W8
+def composite_test_out(homo_output, homo_output2, final_warp_in, occlusion_mask=None):
+    h1, h2, fw = _f32(homo_output), _f32(homo_output2), _f32(final_warp_in)
+    b, _, h, w = h1.shape
+    occ = None if occlusion_mask is None else _f32(occlusion_mask)
+    final_warp = np.empty_like(fw)
+    out2 = np.empty((b, 3, h, w), np.float32)
+    m1, m2 = np.empty_like(out2), np.empty_like(out2)
+    blend = np.empty((b, 3, h, w), np.uint8)
+    _load().o_composite_test_out(_p(h1), _p(h2), _p(fw), _p(occ), _p(final_warp), _p(out2), _p(m1), _p(m2),
+                                 _p(blend), c_int(b), c_int(h), c_int(w))
+    return dict(final_warp_output=final_warp, output1=h1[:, 0:3], output2=out2, mask1=m1, mask2=m2, blend_image=blend)
+
+
+def build_model_arith(warp1, warp2, mask1, mask2, net_out):
+    w1, w2, m1, m2, o = map(_f32, (warp1, warp2, mask1, mask2, net_out))
+    b, _, h, w = w1.shape
+    lm1, lm2, st = np.empty_like(w1), np.empty_like(w1), np.empty_like(w1)
+    _load().o_build_model(_p(w1), _p(w2), _p(m1), _p(m2), _p(o), _p(lm1), _p(lm2), _p(st), c_int(b), c_int(h), c_int(w))
+    return dict(learned_mask1=lm1, learned_mask2=lm2, stitched_image=st)
+
+
+def tps_mix_blend(final_warp, tps_warp, tps_mask, output1, mask1):
+    fw, tw, tm, o1, m1 = map(_f32, (final_warp, tps_warp, tps_mask, output1, mask1))
+    b, _, h, w = fw.shape
+    out2 = np.empty_like(fw)
+    mask2 = np.empty((b, 1, h, w), np.float32)
+    blend = np.empty((b, 3, h, w), np.uint8)
+    _load().o_tps_mix_blend(_p(fw), _p(tw), _p(tm), _p(o1), _p(m1), _p(out2), _p(mask2), _p(blend), c_int(b),
+                            c_int(h), c_int(w))
+    return out2, mask2, blend
+
+
+def overlap_mask(final_warp):
+    fw = _f32(final_warp)
+    b, _, h, w = fw.shape
+    out = np.empty((b, h, w), np.float32)
+    _load().o_overlap_mask(_p(fw), _p(out), c_int(b), c_int(h), c_int(w))
+    return out
+
+
+# ----------------------------------------------------------------- G1 helpers (numpy)
+def tensor_DLT(src_p, dst_p):
+    """torch_DLT.py:17-45 in numpy fp32."""
+    src, dst = _f32(src_p), _f32(dst_p)
+    bs = src.shape[0]
+    ones = np.ones((bs, 4, 1), np.float32)
+    xy1 = np.concatenate((src, ones), 2)
+    zeros = np.zeros_like(xy1)
+    m1 = np.concatenate((np.concatenate((xy1, zeros), 2), np.concatenate((zeros, xy1), 2)), 2).reshape(bs, -1, 6)
+    m2 = np.matmul(dst.reshape(-1, 2, 1), src.reshape(-1, 1, 2)).reshape(bs, -1, 2)
+    a = np.concatenate((m1, -m2), 2)
+    h8 = np.matmul(np.linalg.inv(a), dst.reshape(bs, -1, 1)).reshape(bs, 8)
+    return np.concatenate((h8, ones[:, 0, :]), 1).reshape(bs, 3, 3).astype(np.float32)

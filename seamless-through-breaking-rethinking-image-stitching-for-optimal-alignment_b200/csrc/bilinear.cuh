@@ -4,7 +4,7 @@
 //      evaluated by ATen's vectorised CPU kernel (the oracle's arithmetic):
 //        x_w = floor(x); w = x - x_w; e = 1 - w; n = y - y_n; s = 1 - n
 //        nw = s*e, ne = s*w, sw = n*e, se = n*w
-//        out = ((nw_v*nw + ne_v*ne) + sw_v*sw) + se_v*se    (OOB taps read 0)
+//        out = fma(se_v, se, fma(sw_v, sw, fma(ne_v, ne, nw_v*nw)))   (OOB taps read 0)
 //      used by warp (core/warp_utils.py:77) and bilinear_sampler
 //      (core/utils/utils.py:70).
 //
@@ -47,7 +47,8 @@ struct GridTap {
     return combine(v_nw, v_ne, v_sw, v_se);
   }
   __device__ __forceinline__ float combine(float v_nw, float v_ne, float v_sw, float v_se) const {
-    return fadd(fadd(fadd(fmul(v_nw, nw), fmul(v_ne, ne)), fmul(v_sw, sw)), fmul(v_se, se));
+    // ATen's CPU build contracts the mul/add chain into FMAs (bit-exact vs F.grid_sample)
+    return __fmaf_rn(v_se, se, __fmaf_rn(v_sw, sw, __fmaf_rn(v_ne, ne, fmul(v_nw, nw))));
   }
 };
 

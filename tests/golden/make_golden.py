@@ -1,0 +1,257 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own Python functions.
+
+Run here (the build container), where the reference is mounted read-only at
+/root/reference:      python tests/golden/make_golden.py
+The GPU box has no /root/reference: tests only read the committed .npz files.
+
+Import shims: fake `skimage`, fake `timm.*` (import-time only,
+none of the stubbed symbols executes on the path), `.cuda()` -> identity on this
+GPU-less box, and an attribute-bag config in place of yacs.CfgNode.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("STITCH_REFERENCE", "/root/reference")
+sys.path.insert(0, HERE)
+import cases  # noqa: E402
+
+
+def install_shims():
+    sys.path[:0] = [REF, os.path.join(REF, "core")]
+    for name in ("skimage", "skimage.io"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["skimage"].io = sys.modules["skimage.io"]
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _Dummy(torch.nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    timm = mod("timm", create_model=lambda *a, **k: None)
+    mod("timm.data", IMAGENET_DEFAULT_MEAN=(0.485, 0.456, 0.406), IMAGENET_DEFAULT_STD=(0.229, 0.224, 0.225))
+    layers = mod("timm.models.layers", Mlp=_Dummy, DropPath=_Dummy, to_2tuple=lambda x: (x, x),
+                 trunc_normal_=lambda *a, **k: None, activations=types.SimpleNamespace())
+    models = mod("timm.models", layers=layers)
+    mod("timm.models.registry", register_model=lambda f: f)
+    mod("timm.models.vision_transformer", Attention=_Dummy, Block=_Dummy, _cfg=lambda **k: {})
+    timm.models = models
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+
+
+def capture_gather_indices(fn, *args, **kw):
+    """Run fn while recording the index tensors of its four torch.gather calls
+    (idx_a..idx_d of the UDIS sampler, torch_homo_transform.py:54-79)."""
+    rec = []
+    orig = torch.gather
+
+    def spy(inp, dim, index, *a, **k):
+        rec.append(index[:, 0].clone())
+        return orig(inp, dim, index, *a, **k)
+
+    torch.gather = spy
+    try:
+        out = fn(*args, **kw)
+    finally:
+        torch.gather = orig
+    return out, rec
+
+
+def decode_indices(rec, b, h, w, hout, wout):
+    """idx_a = base + y0*W + x0, idx_b = base + y1*W + x0, idx_c = base + y0*W + x1 -> (x0,x1,y0,y1)."""
+    ia, ib, ic, _ = [r.reshape(b, hout, wout) for r in rec]
+    base = (torch.arange(b) * (h * w)).view(b, 1, 1)
+    ia, ib, ic = ia - base, ib - base, ic - base
+    x0, y0 = ia % w, ia // w
+    y1 = ib // w
+    x1 = ic % w
+    return torch.stack([x0, x1, y0, y1], 1).to(torch.int32).numpy()
+
+
+def save(name, inputs_checksum, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, inputs_checksum=np.float64(inputs_checksum), **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def main():
+    install_shims()
+    from types import SimpleNamespace
+    import core.warp_utils as ref_wu
+    import core.udis_utils.torch_homo_transform as ref_homo
+    import core.udis_utils.torch_tps_transform as ref_tps
+    import core.udis_utils.torch_DLT as ref_dlt
+    import core.utils.utils as ref_utils
+    from core.FlowFormer.PerCostFormer3.encoder import MemoryEncoder
+    from core.FlowFormer.PerCostFormer3.decoder import MemoryDecoder
+    import core.flowHomoAdpater as ref_ad
+    from core.UDIS2.Composition.network import build_model as ref_build_model
+
+    enc_self = SimpleNamespace(cfg=SimpleNamespace(cost_heads_num=1))
+    torch.set_grad_enabled(False)
+
+    # ---------------------------------------------------------------- C1
+    for name, fn in (("corr_small", cases.corr_small), ("corr_c64", cases.corr_c64)):
+        c = fn()
+        vol = MemoryEncoder.corr(enc_self, c["fmap1"], c["fmap2"])
+        save(name, cases.checksum(*c.values()), vol=vol.numpy())
+    c = cases.corr_512()
+    vol = MemoryEncoder.corr(enc_self, c["fmap1"], c["fmap2"])
+    v2 = vol.reshape(4096, 4096)
+    cm = vol.permute(0, 2, 3, 1, 4, 5).contiguous().view(4096, 1, 64, 64)      # encoder.py:260
+    # pyramid (C2): no reference implementation — F.avg_pool2d chained (encoder.py:376 hint)
+    l1 = F.avg_pool2d(cm, 2, stride=2); l2 = F.avg_pool2d(l1, 2, stride=2); l3 = F.avg_pool2d(l2, 2, stride=2)
+    save("corr_512", cases.checksum(*c.values()), vol_sample=v2[cases.CORR_512_ROWS, cases.CORR_512_COLS].numpy(),
+         vol_absmax=np.float32(v2.abs().max()), vol_rms=np.float32(v2.pow(2).mean().sqrt()),
+         lvl1_sample=l1[::97].numpy(), lvl2_sample=l2[::97].numpy(), lvl3_sample=l3[::97].numpy())
+
+    # ---------------------------------------------------------------- C3
+    for name, fn in (("lookup_small", cases.lookup_small), ("lookup_64", cases.lookup_64)):
+        c = fn()
+        out = MemoryDecoder.encode_flow_token(None, c["cost_maps"], c["coords"])
+        extra = {}
+        if name == "lookup_small":
+            extra["out_r2"] = MemoryDecoder.encode_flow_token(None, c["cost_maps"], c["coords"], r=2).numpy()
+            # C3p convention (common.py:245-248): centroid / 2**i + delta on pooled maps
+            pyr = [c["cost_maps"]]
+            for _ in range(2):
+                pyr.append(F.avg_pool2d(pyr[-1], 2, stride=2))
+            outs = [MemoryDecoder.encode_flow_token(None, pm, c["coords"] / 2 ** i) for i, pm in enumerate(pyr)]
+            extra["out_pyramid"] = torch.cat(outs, 1).numpy()
+        save(name, cases.checksum(*c.values()), out=out.contiguous().numpy(),
+             out_strides=np.array(out.stride()), **extra)
+    c = cases.lookup_small()
+    pts = torch.rand(3, 7, 9, 2, generator=torch.Generator().manual_seed(5)) * 30 - 3
+    img = torch.randn(3, 4, 16, 24, generator=torch.Generator().manual_seed(6))
+    samp, msk = ref_utils.bilinear_sampler(img, pts, mask=True)
+    save("bilinear_sampler", cases.checksum(img, pts), img=img.numpy(), pts=pts.numpy(), out=samp.numpy(), mask=msk.numpy())
+
+    # ---------------------------------------------------------------- W1
+    for name, fn in (("warp_small", cases.warp_small), ("warp_flow2", cases.warp_flow2)):
+        c = fn()
+        save(name, cases.checksum(*c.values()), out=ref_wu.warp(c["x"], c["flo"]).numpy())
+    c = cases.warp_512()
+    out = ref_wu.warp(c["x"], c["flo"])
+    save("warp_512", cases.checksum(*c.values()), out_sample=out[..., cases.WARP_512_SAMPLE[0], cases.WARP_512_SAMPLE[1]].numpy())
+
+    # ---------------------------------------------------------------- W2
+    for name, fn in (("homo_small", cases.homo_small), ("homo_theta1", cases.homo_theta1),
+                     ("homo_degenerate", cases.homo_degenerate)):
+        c = fn()
+        out, rec = capture_gather_indices(ref_homo.transformer, c["U"], c["theta"], c["out_size"])
+        b, _, h, w = c["U"].shape
+        idx = decode_indices(rec, b, h, w, *c["out_size"])
+        save(name, cases.checksum(c["U"], c["theta"]), out=out.contiguous().numpy(), idx=idx)
+    c = cases.homo_512()
+    out, rec = capture_gather_indices(ref_homo.transformer, c["U"], c["theta"], c["out_size"])
+    idx = decode_indices(rec, 1, 512, 512, 512, 512)
+    sy, sx = cases.HOMO_512_SAMPLE
+    save("homo_512", cases.checksum(c["U"], c["theta"]), out_sample=out[..., sy, sx].contiguous().numpy(),
+         idx_sample=idx[..., sy, sx], mask_bits=np.packbits((out[0, 3] > 0.5).numpy()))
+
+    # ---------------------------------------------------------------- W3
+    c = cases.tps_small()
+    out, rec = capture_gather_indices(ref_tps.transformer, c["U"], c["source"], c["target"], c["out_size"])
+    b, _, h, w = c["U"].shape
+    idx = decode_indices(rec, b, h, w, *c["out_size"])
+    save("tps_small", cases.checksum(c["U"], c["source"], c["target"]), out=out.contiguous().numpy(), idx=idx)
+
+    # ---------------------------------------------------------------- W4
+    for name, fn in (("range_small", cases.range_small), ("range_smooth", cases.range_smooth)):
+        c = fn()
+        rm = ref_wu.compute_range_map(c["flow_ji"])
+        occ = ref_wu.compute_occlusion(c["flow_ij"], c["flow_ji"], "wang", occlusion_are_zeros=True, boundaries_occluded=True)
+        occ_nz = ref_wu.compute_occlusion(c["flow_ij"], c["flow_ji"], "wang", occlusion_are_zeros=False, boundaries_occluded=True)
+        occ_nb = ref_wu.compute_occlusion(c["flow_ij"], c["flow_ji"], "wang", occlusion_are_zeros=True, boundaries_occluded=False)
+        brox = ref_wu.compute_occlusion(c["flow_ij"], c["flow_ji"], "brox")
+        save(name, cases.checksum(*c.values()), range_map=rm.numpy(), occ=occ.numpy(), occ_nz=occ_nz.numpy(),
+             occ_nb=occ_nb.numpy(), brox=brox.numpy())
+
+    # ---------------------------------------------------------------- W5
+    for name, fn in (("morph_small", cases.morph_small), ("morph_big", cases.morph_big)):
+        c = fn()
+        out = ref_ad.preprocess_occlusion_mask(c["mask"])
+        out7 = ref_ad.preprocess_occlusion_mask(c["mask"], kernel_size=(7, 11))
+        save(name, cases.checksum(c["mask"]), out_bits=np.packbits(out.numpy() > 0.5), out7_bits=np.packbits(out7.numpy() > 0.5),
+             shape=np.array(out.shape))
+
+    # ---------------------------------------------------------------- W7
+    c = cases.build_model_small()
+    r = ref_build_model(lambda *a: c["net_out"], c["warp1"], c["warp2"], c["mask1"], c["mask2"])
+    save("build_model", cases.checksum(*c.values()), **{k: v.numpy() for k, v in r.items()})
+
+    # ---------------------------------------------------------------- W8 (restated: tps_pipline.py needs matplotlib
+    # + cv2-contrib at import/run time; lines :139-170 are restated here with the same torch / cv2 calls)
+    import cv2
+    c = cases.tps_mix_small()
+    tm = c["tps_mask3"].mean(dim=1, keepdim=True)
+    tm = (tm >= 0.5).float()
+    inv = (1.0 - tm)[0, 0].numpy()
+    kernel = cv2.getStructuringElement(cv2.MORPH_RECT, (11, 11))
+    inv = cv2.dilate(cv2.erode(inv, kernel), kernel)
+    tm = 1.0 - torch.tensor(inv)[None, None]
+    tps_warp = c["tps_warp_raw"] * tm
+    fm = (c["final_warp"] >= 3).float().mean(dim=1, keepdim=True)
+    fm = (fm >= 0.5).float()
+    inv1 = ((1 - c["mask1"]).float().mean(dim=1, keepdim=True) >= 0.5).float()
+    tfw = c["final_warp"] * fm + tps_warp * (1 - fm) * inv1
+    tfm = fm + (1 - fm) * tm * inv1
+    out2 = tfw * tfm
+    blend = ((c["output1"] * c["mask1"] + out2 * tfm) / (c["mask1"] + tfm)).clip(0, 255).to(torch.uint8)
+    save("tps_mix", cases.checksum(*c.values()), tps_mask=tm.numpy(), output2=out2.numpy(), mask2=tfm.numpy(), blend=blend.numpy())
+
+    # ---------------------------------------------------------------- G1
+    g = torch.Generator().manual_seed(77)
+    src = torch.tensor([[0.0, 0.0], [64, 0.0], [0.0, 48], [64, 48]]).unsqueeze(0).expand(3, -1, -1)
+    dst = src + torch.randn(3, 4, 2, generator=g) * 4
+    Hm = ref_dlt.tensor_DLT(src, dst)
+    mesh = ref_wu.H2Mesh(Hm, ref_wu.get_rigid_mesh(3, 48, 64, 7, 9), 7, 9)
+    fl = torch.randn(2, 2, 16, 20, generator=g)
+    save("geometry", cases.checksum(dst), dst=dst.numpy(), H=Hm.numpy(), mesh=mesh.numpy(), flow=fl.numpy(),
+         flow_resized=ref_wu.resize_flow(fl.clone(), (37, 45)).numpy())
+
+    # ---------------------------------------------------------------- adapter forwards (stub networks)
+    c = cases.adapter_train_eval()
+    ad = ref_ad.FlowHomoAdpater(cases.StubHomo(c["offsets"]), cases.StubFlow(c["flows"]), cases.adapter_cfg())
+    ad.eval()
+    od = ad.train_eval_foward(c["image1"], c["image2"])
+    save("adapter_train_eval", cases.checksum(c["image1"], c["image2"], c["offsets"], *c["flows"]),
+         output_H=od["output_H"].contiguous().numpy(), output_H_inv=od["output_H_inv"].contiguous().numpy(),
+         final_warp_output=od["final_warp_output"].numpy(), overlap=od["overlap"].numpy(),
+         origin_occlusion_mask=od["origin_occlusion_mask"].numpy(), H=od["H"].numpy())
+
+    c = cases.adapter_test_out()
+    ad = ref_ad.FlowHomoAdpater(cases.StubHomo(c["offsets"]), cases.StubFlow(c["flows"]), cases.adapter_cfg())
+    ad.eval()
+    od = ad.test_out_forward(c["image1"], c["image2"])
+    sy, sx = cases.ADAPTER_SAMPLE
+    arrays = {}
+    for k in ("H_warp", "final_warp", "output1", "output2", "mask1", "mask2", "H_warp_mask"):
+        arrays[k + "_sample"] = od[k][..., sy, sx].contiguous().numpy()
+    arrays["blend_image_sample"] = od["blend_image"][..., sy, sx].contiguous().numpy()
+    for k in ("occlusion_mask", "origin_occlusion_mask", "warp_input2_mask"):
+        arrays[k + "_bits"] = np.packbits(od[k].numpy() > 0.5)
+        arrays[k + "_shape"] = np.array(od[k].shape)
+    arrays["mask1_bits"] = np.packbits(od["mask1"].numpy() > 0.5)
+    arrays["mask2_bits"] = np.packbits(od["mask2"].numpy() > 0.5)
+    arrays["canvas"] = np.array([od["width_min"], od["height_min"], od["out_height"], od["out_width"]])
+    arrays["H"] = od["H"].numpy()
+    arrays["I_mat"] = od["I_mat"].numpy()
+    save("adapter_test_out", cases.checksum(c["image1"], c["image2"], c["offsets"], *c["flows"]), **arrays)
+
+
+if __name__ == "__main__":
+    main()

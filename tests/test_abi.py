@@ -1,0 +1,73 @@
+"""CPU: the C-ABI shared library loads and exports every symbol that
+include/stitch_b200.h declares; compute entry points refuse to run without a B200."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import stitch_b200
+    return stitch_b200._lib.load()
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "stitch_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported(lib):
+    import stitch_b200
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/stitch_b200.h but not exported"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(stitch_b200._lib.SIGNATURES) == names
+
+
+def test_version_and_error_string(lib):
+    assert lib.sb_version() == 100
+    assert isinstance(lib.sb_last_error(), (bytes, type(None)))
+
+
+def test_sm100a_only_binary():
+    import subprocess
+    import stitch_b200
+    try:
+        out = subprocess.run(["cuobjdump", "-lelf", stitch_b200._lib.LIB_PATH], capture_output=True, text=True).stdout
+    except FileNotFoundError:
+        pytest.skip("cuobjdump not available")
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    import stitch_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    # the ABI itself reports the missing device instead of computing anything
+    assert lib.sb_device_check() != 0
+    assert lib.sb_flow_warp(None, None, None, None, None, 1, 1, 1, 1, None) != 0
+    assert b"" != lib.sb_last_error()
+    # and the Python surface refuses CPU tensors outright
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        stitch_b200.warp(torch.zeros(1, 6, 8, 8), torch.zeros(1, 2, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        stitch_b200.corr_volume(torch.zeros(1, 64, 4, 4), torch.zeros(1, 64, 4, 4))
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the oracle."""
+    pkg = os.path.join(ROOT, "seamless-through-breaking-rethinking-image-stitching-for-optimal-alignment_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "stitch_oracle" not in src and "liboracle" not in src, f

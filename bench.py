@@ -192,19 +192,44 @@ def run_ours(args):
     for _ in range(args.warmup):
         hp.step(pb_dev)
     barrier()
+    run_step = lambda: hp.step(pb_dev)
+    _lib.reset_launch_count()
+    hp.step(pb_dev)
+    launches_per_step_eager = _lib.launch_count()
+    if args.graph:
+        # the step is sync-free: capture its launches once, replay as one submission
+        hp.capture(pb_dev)
+        run_step = hp.replay
+        for _ in range(2):
+            run_step()
+        barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     _lib.reset_launch_count()
-    hp.gemm_events = []
+    hp.gemm_events = None if args.graph else []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        out = hp.step(pb_dev)
+        out = run_step()
     e1.record(stream)
     barrier()
     launches = _lib.launch_count()
     ms_total = e0.elapsed_time(e1)
+    if args.graph:
+        # events cannot be timed inside a captured graph: the dominant kernel's launches are
+        # timed in an eager pass of the same steps right after (same inputs, same stream)
+        launches = launches_per_step_eager * args.steps
+        hp.gemm_events = []
+        eg0, eg1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eg0.record(stream)
+        for _ in range(args.steps):
+            hp.step(pb_dev)
+        eg1.record(stream)
+        barrier()
+        ms_eager_total = eg0.elapsed_time(eg1)
+    else:
+        ms_eager_total = ms_total
     gemm_ms = [a.elapsed_time(b) for a, b in hp.gemm_events]
     hp.gemm_events = None
     clocks = sampler.stop() if rank == 0 else None
@@ -218,14 +243,17 @@ def run_ours(args):
     # ---------------- end to end through the public API with HOST buffers (`e2e`)
     out_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
                 for k in ("final_warp_output", "overlap", "origin_occlusion_mask")}
-    tok_host = torch.empty((2 * ITERS,) + tuple(out["cost_tokens"][0].shape), dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        pbd = pb_host.map(lambda t: t.to(dev, non_blocking=True))          # H2D of this step's inputs
-        o = hp.step(pbd)
+        if args.graph:
+            for d, h in zip(pb_dev.tensors(), pb_host.tensors()):            # H2D into the graph's static inputs
+                d.copy_(h, non_blocking=True)
+            o = hp.replay()
+        else:
+            pbd = pb_host.map(lambda t: t.to(dev, non_blocking=True))      # H2D of this step's inputs
+            o = hp.step(pbd)
         for k, h in out_host.items():                                        # D2H of the step's results
-            h.copy_(o[k], non_blocking=True)
-        tok_host.copy_(torch.stack([x.contiguous() for x in o["cost_tokens"]]), non_blocking=True)
+            h.copy_(o[k], non_blocking=True)                                 # (what evaluate.py:44-53 moves to the host)
 
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
@@ -242,7 +270,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = pairs_total / (t.item() / 1000.0)
     h2d = pb_host.nbytes()
-    d2h = sum(h.numel() * h.element_size() for h in out_host.values()) + tok_host.numel() * 4
+    d2h = sum(h.numel() * h.element_size() for h in out_host.values())
 
     # ---------------- the single collective of the path: final metric reduction
     metric_sum = torch.tensor([out["final_warp_output"].double().mean().item(), float(B)], dtype=torch.float64, device=dev)
@@ -280,7 +308,8 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(world), "global_batch": B * world, "image_size": SIZE,
-                       "lookup_iters": ITERS, "parallelism": f"pairs sharded x{world}, no data-path collective",
+                       "lookup_iters": ITERS, "submission": "cuda-graph replay" if args.graph else "eager launches",
+                       "parallelism": f"pairs sharded x{world}, no data-path collective",
                        "l2": "per-step working set (2 x 1 GiB volumes) >> 126 MB L2, no explicit flush",
                        "algorithmic_bytes_per_step": work["bytes"], "algorithmic_flops_per_step": work["flops"]},
             "roofline": {"bound": "hbm", "kernel": "corr_umma_kernel<true> (tcgen05 cost volume + fused pyramid)",
@@ -290,7 +319,8 @@ def run_ours(args):
                          "tensor_tflops": gemm_flops / (gemm_avg_ms / 1000.0) / 1e12,
                          "tensor_frac_of_sustained": (gemm_flops / (gemm_avg_ms / 1000.0) / 1e12) /
                          float(peaks.get("bf16_tflops_sustained", 1400.0)),
-                         "kernel_share_of_step": sum(gemm_ms) / ms_total if gemm_ms else None},
+                         "kernel_share_of_step": sum(gemm_ms) / ms_eager_total if gemm_ms else None,
+                         "timed": "CUDA events around every launch, eager pass" + (" after the graph-replay region" if args.graph else " = the timed region")},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "wall_ms_per_step": wall_ms / args.steps},
@@ -310,6 +340,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the step as one captured CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

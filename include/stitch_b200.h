@@ -142,10 +142,25 @@ int sb_flow_warp(const float* x, const float* flo, const float* mul_mask, float*
  *   out [B,C,Hout,Wout].
  *   idx_dbg: optional int32 [B,4,Hout,Wout] receiving the clamped integer
  *   grid indices (x0,x1,y0,y1) — the "integer grid indices" of the parity
- *   contract; NULL to skip. */
+ *   contract; NULL to skip.
+ *   n_ones: the reference always warps cat(image, ones) (flowHomoAdpater.py:110-113,
+ *   292,310,314); with n_ones > 0 the kernel behaves as if U had n_ones extra
+ *   all-ones planes appended (out has C + n_ones channels) without reading them. */
 int sb_homo_warp(const float* U, const float* theta, const float* xs, const float* ys,
                  float* out, int32_t* idx_dbg,
-                 int B, int C, int H, int W, int Hout, int Wout, int theta_batch,
+                 int B, int C, int n_ones, int H, int W, int Hout, int Wout, int theta_batch,
+                 sb_stream_t stream);
+
+/* ------------------------------------------------------------------ G1
+ * Fused geometry of the adapter: tensor_DLT (core/udis_utils/torch_DLT.py:17-45)
+ * + the normalised-coordinate products of core/flowHomoAdpater.py:96-113, one
+ * launch, no host synchronisation (torch.inverse synchronises):
+ *   H = DLT(src_p, dst_p) [B,3,3];  theta = L*H*R;  theta_inv = L*H^-1*R.
+ * src_p, dst_p: DEVICE [B,4,2]; L_host, R_host: HOST pointers to 9 floats
+ * (row-major 3x3, passed to the kernel by value); H / theta / theta_inv:
+ * DEVICE [B,3,3], each optional (NULL to skip). */
+int sb_dlt_theta(const float* src_p, const float* dst_p, const float* L_host,
+                 const float* R_host, float* H, float* theta, float* theta_inv, int B,
                  sb_stream_t stream);
 
 /* ------------------------------------------------------------------ W3

@@ -30,11 +30,6 @@ def _flag(cfg, name, default=False):
     return getattr(cfg, name) if hasattr(cfg, name) else default
 
 
-def _norm_matrix(w, h, device):
-    """M maps normalised [-1,1] coordinates to pixels of a w x h image."""
-    return torch.tensor([[w / 2.0, 0.0, w / 2.0], [0.0, h / 2.0, h / 2.0], [0.0, 0.0, 1.0]], device=device)
-
-
 def _resize_512(x):
     """The reference uses torchvision ``T.Resize((512,512))`` (identity at 512^2).
     Its pinned torchvision 0.13 does plain bilinear (no antialias) on tensors."""
@@ -85,19 +80,14 @@ class FlowHomoAdpater(nn.Module):
         out_dict = {}
 
         h_motion = self.predict_homo(input1_tensor, input2_tensor)
-        src_p = torch.tensor([[0.0, 0.0], [img_w, 0.0], [0.0, img_h], [img_w, img_h]], device=dev)
-        src_p = src_p.unsqueeze(0).expand(b, -1, -1)
+        src_p = torch_DLT.corner_points(img_w, img_h, b, dev)
         dst_p = src_p + h_motion
-        H = torch_DLT.tensor_DLT(src_p / 8, dst_p / 8)                              # :96
-        M = _norm_matrix(img_w / 8, img_h / 8, dev)
-        M_inv = torch.inverse(M)
-        H_mat = M_inv.expand(b, -1, -1) @ H @ M.expand(b, -1, -1)                  # :108
-        H_inv_mat = M_inv.expand(b, -1, -1) @ torch.inverse(H) @ M.expand(b, -1, -1)
-
-        ones = torch.ones_like(input2_tensor)
-        output_H = torch_homo_transform.transformer(torch.cat((input2_tensor, ones), 1), H_mat, (img_h, img_w))
-        output_H_inv = torch_homo_transform.transformer(torch.cat((input1_tensor, ones), 1), H_inv_mat,
-                                                        (img_h, img_w))
+        # :96-113 in one launch: H = DLT(src/8, dst/8); H_mat = M^-1 H M; H_inv_mat = M^-1 H^-1 M
+        M = torch_DLT.norm_matrix(img_w / 8, img_h / 8)
+        H, H_mat, H_inv_mat = torch_DLT.dlt_thetas(src_p / 8, dst_p / 8, left=torch_DLT._inv3(M), right=M)
+        # the all-ones mask planes of cat(image, ones) are synthesised inside the kernel
+        output_H = torch_homo_transform.transformer(input2_tensor, H_mat, (img_h, img_w), append_ones=3)
+        output_H_inv = torch_homo_transform.transformer(input1_tensor, H_inv_mat, (img_h, img_w), append_ones=3)
         if _flag(cfg, "only_homo"):
             final_warp_output, flow_predictions, overlap = output_H, None, None
         else:
@@ -129,12 +119,11 @@ class FlowHomoAdpater(nn.Module):
         # ---- networks at 512 x 512 (:203-238)
         in1_512, in2_512 = _resize_512(input1_tensor), _resize_512(input2_tensor)
         h_motion_512 = self.predict_homo(in1_512, in2_512)
-        src512 = torch.tensor([[0.0, 0.0], [512, 0.0], [0.0, 512], [512, 512]], device=dev).unsqueeze(0).expand(b, -1, -1)
-        H512 = torch_DLT.tensor_DLT(src512, src512 + h_motion_512)
-        M512 = _norm_matrix(512, 512, dev)
-        H_mat512 = torch.inverse(M512).expand(b, -1, -1) @ H512 @ M512.expand(b, -1, -1)
-        output_H512 = torch_homo_transform.transformer(torch.cat((in2_512, torch.ones_like(in2_512)), 1),
-                                                       H_mat512, (512, 512))
+        src512 = torch_DLT.corner_points(512, 512, b, dev)
+        M512 = torch_DLT.norm_matrix(512, 512)
+        _, H_mat512, _ = torch_DLT.dlt_thetas(src512, src512 + h_motion_512, left=torch_DLT._inv3(M512), right=M512,
+                                              want_inverse=False)
+        output_H512 = torch_homo_transform.transformer(in2_512, H_mat512, (512, 512), append_ones=3)
         warp_in2_512 = output_H512[:, 0:3]
         warp_in2_mask_512 = (output_H512[:, 3:6].mean(dim=1, keepdim=True) > 0.5).to(output_H512.dtype)
         flow_512 = self.predict_flow(in1_512, warp_in2_512)
@@ -142,9 +131,9 @@ class FlowHomoAdpater(nn.Module):
         # ---- rescale flow and H to the native resolution (:241-255)
         flow_predictions = [warp_utils.resize_flow(f, new_shape=(img_h, img_w)) for f in flow_512]
         h_motion = torch.stack([h_motion_512[..., 0] * img_w / 512, h_motion_512[..., 1] * img_h / 512], 2)
-        src_p = torch.tensor([[0.0, 0.0], [img_w, 0.0], [0.0, img_h], [img_w, img_h]], device=dev)
-        src_p = src_p.unsqueeze(0).expand(b, -1, -1)
-        H = torch_DLT.tensor_DLT(src_p, src_p + h_motion)
+        src_p = torch_DLT.corner_points(img_w, img_h, b, dev)
+        dst_p = src_p + h_motion
+        H = torch_DLT.tensor_DLT(src_p, dst_p)
         mesh = warp_utils.H2Mesh(H, warp_utils.get_rigid_mesh(b, img_h, img_w, device=dev))
 
         # ---- canvas (:259-271): one bounding box for the whole batch (host sync, as in the reference)
@@ -154,23 +143,22 @@ class FlowHomoAdpater(nn.Module):
         height_max, height_min = int(max(float(img_h), h_max)), int(min(0.0, h_min))
         out_width, out_height = width_max - width_min, height_max - height_min
 
-        # ---- image 1 on the canvas (:273-292)
-        M = _norm_matrix(out_width, out_height, dev)
-        N_inv = torch.inverse(_norm_matrix(img_w, img_h, dev))
-        I_ = torch.tensor([[1.0, 0.0, width_min], [0.0, 1.0, height_min], [0.0, 0.0, 1.0]], device=dev)
-        I_mat = (N_inv @ I_ @ M).unsqueeze(0)
-        homo_output = torch_homo_transform.transformer(
-            torch.cat((input1_tensor, torch.ones_like(input1_tensor)), 1), I_mat, (out_height, out_width))
+        # ---- image 1 on the canvas (:273-292); the 3x3 constants are host floats
+        import numpy as np
+        M = np.array(torch_DLT.norm_matrix(out_width, out_height), np.float32).reshape(3, 3)
+        N_inv = np.linalg.inv(np.array(torch_DLT.norm_matrix(img_w, img_h), np.float32).reshape(3, 3)).astype(np.float32)
+        I_ = np.array([[1.0, 0.0, width_min], [0.0, 1.0, height_min], [0.0, 0.0, 1.0]], np.float32)
+        I_mat_np = (N_inv @ I_ @ M).astype(np.float32)
+        I_mat = torch.from_numpy(I_mat_np).to(dev).unsqueeze(0)
+        homo_output = torch_homo_transform.transformer(input1_tensor, I_mat, (out_height, out_width), append_ones=3)
 
-        # ---- image 2: homography then residual flow (:303-317)
-        H = H @ I_.unsqueeze(0)
-        H_mat = N_inv.expand(b, -1, -1) @ H @ M.expand(b, -1, -1)
-        homo_output2 = torch_homo_transform.transformer(
-            torch.cat((input2_tensor, torch.ones_like(input2_tensor)), 1), H_mat, (out_height, out_width))
+        # ---- image 2: homography then residual flow (:303-317).  H <- H @ I_ ; H_mat = N^-1 H M
+        H, H_mat, _ = torch_DLT.dlt_thetas(src_p, dst_p, left=N_inv.reshape(-1).tolist(),
+                                           right=(I_ @ M).astype(np.float32).reshape(-1).tolist(), want_inverse=False)
+        H = H @ torch.from_numpy(I_).to(dev).unsqueeze(0)
+        homo_output2 = torch_homo_transform.transformer(input2_tensor, H_mat, (out_height, out_width), append_ones=3)
         residual_flow = flow_predictions[-1]
-        flow_mask = torch.ones_like(residual_flow[:, :1])
-        rf_out = torch_homo_transform.transformer(torch.cat((residual_flow, flow_mask), 1), I_mat,
-                                                  (out_height, out_width))
+        rf_out = torch_homo_transform.transformer(residual_flow, I_mat, (out_height, out_width), append_ones=1)
         # warp by the residual flow and multiply by the flow mask in the same pass (:316-317)
         final_warp_in = warp_utils.warp(homo_output2, rf_out[:, 0:2], mul_mask=rf_out[:, 2:3])
 

@@ -57,7 +57,6 @@ def corr(fmap1: torch.Tensor, fmap2: torch.Tensor, heads: int = 1, pyramid_level
         rc = lib.sb_corr(_lib.ptr(v1), _lib.ptr(v2), _lib.ptr(vol), _lib.ptr(lv[0]), _lib.ptr(lv[1]),
                          _lib.ptr(lv[2]), _lib.ptr(ws), ws.numel(), bh, d, h1, w1, h2, w2, _lib.stream_ptr())
         _lib.check(rc, "sb_corr")
-        ws.record_stream(torch.cuda.current_stream())
     out = vol.view(b, heads, h1, w1, h2, w2)
     if pyramid_levels:
         return out, [x for x in lv[:pyramid_levels]]

@@ -177,11 +177,12 @@ extern "C" int sb_composite_test_out(const float* homo1, const float* homo2, con
                                      int W, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(homo1 && homo2 && fw_in && final_warp && output2 && mask1 && mask2 && blend,
-             SB_EINVAL, "sb_composite_test_out: null pointer");
+  
   SB_REQUIRE(B >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_composite_test_out: bad size");
   const long long plane = (long long)H * W, total = plane * B;
   if (total == 0) return SB_OK;
+  SB_REQUIRE(homo1 && homo2 && fw_in && final_warp && output2 && mask1 && mask2 && blend,
+             SB_EINVAL, "sb_composite_test_out: null pointer");
   composite_test_out_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
       homo1, homo2, fw_in, occ, final_warp, output2, mask1, mask2, blend, plane, total);
   SB_LAUNCH_CHECK("composite_test_out_kernel");
@@ -194,11 +195,12 @@ extern "C" int sb_build_model(const float* warp1, const float* warp2, const floa
                               sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(warp1 && warp2 && mask1 && mask2 && net_out && learned_mask1 && learned_mask2 && stitched,
-             SB_EINVAL, "sb_build_model: null pointer");
+  
   SB_REQUIRE(B >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_build_model: bad size");
   const long long plane = (long long)H * W, total = plane * B * 3;
   if (total == 0) return SB_OK;
+  SB_REQUIRE(warp1 && warp2 && mask1 && mask2 && net_out && learned_mask1 && learned_mask2 && stitched,
+             SB_EINVAL, "sb_build_model: null pointer");
   build_model_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
       warp1, warp2, mask1, mask2, net_out, learned_mask1, learned_mask2, stitched, plane, total);
   SB_LAUNCH_CHECK("build_model_kernel");
@@ -211,11 +213,12 @@ extern "C" int sb_tps_mix_blend(const float* final_warp, const float* tps_warp,
                                 sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(final_warp && tps_warp && tps_mask && output1 && mask1 && output2 && mask2 && blend,
-             SB_EINVAL, "sb_tps_mix_blend: null pointer");
+  
   SB_REQUIRE(B >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_tps_mix_blend: bad size");
   const long long plane = (long long)H * W, total = plane * B;
   if (total == 0) return SB_OK;
+  SB_REQUIRE(final_warp && tps_warp && tps_mask && output1 && mask1 && output2 && mask2 && blend,
+             SB_EINVAL, "sb_tps_mix_blend: null pointer");
   tps_mix_blend_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(
       final_warp, tps_warp, tps_mask, output1, mask1, output2, mask2, blend, plane, total);
   SB_LAUNCH_CHECK("tps_mix_blend_kernel");
@@ -226,10 +229,11 @@ extern "C" int sb_overlap_mask(const float* final_warp, float* overlap, int B, i
                                sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(final_warp && overlap, SB_EINVAL, "sb_overlap_mask: null pointer");
+  
   SB_REQUIRE(B >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_overlap_mask: bad size");
   const long long plane = (long long)H * W, total = plane * B;
   if (total == 0) return SB_OK;
+  SB_REQUIRE(final_warp && overlap, SB_EINVAL, "sb_overlap_mask: null pointer");
   overlap_mask_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(final_warp, overlap, plane, total);
   SB_LAUNCH_CHECK("overlap_mask_kernel");
   return SB_OK;

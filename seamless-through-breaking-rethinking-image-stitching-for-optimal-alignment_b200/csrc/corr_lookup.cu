@@ -135,7 +135,7 @@ extern "C" int sb_corr_lookup(const float* cost_maps, const float* coords, float
                               int out_stride, int out_offset, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(cost_maps && coords && out, SB_EINVAL, "sb_corr_lookup: null pointer");
+  
   SB_REQUIRE(B >= 0 && H1 >= 0 && W1 >= 0 && H2 > 0 && W2 > 0, SB_EINVAL,
              "sb_corr_lookup: bad size");
   SB_REQUIRE(r >= 0 && r <= kMaxR, SB_EUNSUP, "sb_corr_lookup: r=%d outside [0,%d]", r, kMaxR);
@@ -146,6 +146,7 @@ extern "C" int sb_corr_lookup(const float* cost_maps, const float* coords, float
   SB_REQUIRE((long long)H2 * W2 < (1ll << 31), SB_EUNSUP, "sb_corr_lookup: map too large");
   const long long nq = (long long)B * H1 * W1;
   if (nq == 0) return SB_OK;
+  SB_REQUIRE(cost_maps && coords && out, SB_EINVAL, "sb_corr_lookup: null pointer");
   long long blocks = (nq + kLookupWarps - 1) / kLookupWarps;
   const long long max_blocks = (long long)kNumSMs * 8 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
@@ -159,12 +160,13 @@ extern "C" int sb_bilinear_sampler(const float* img, const float* coords, float*
                                    int H, int W, int Ho, int Wo, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(img && coords && out, SB_EINVAL, "sb_bilinear_sampler: null pointer");
+  
   SB_REQUIRE(N >= 0 && C >= 0 && H > 0 && W > 0 && Ho >= 0 && Wo >= 0, SB_EINVAL,
              "sb_bilinear_sampler: bad size");
   SB_REQUIRE((long long)H * W < (1ll << 31), SB_EUNSUP, "sb_bilinear_sampler: plane too large");
   const long long HoWo = (long long)Ho * Wo, total = (long long)N * HoWo;
   if (total == 0 || C == 0) return SB_OK;
+  SB_REQUIRE(img && coords && out, SB_EINVAL, "sb_bilinear_sampler: null pointer");
   long long blocks = (total + 255) / 256;
   const long long max_blocks = (long long)kNumSMs * 8 * 16;
   if (blocks > max_blocks) blocks = max_blocks;

@@ -63,12 +63,13 @@ extern "C" int sb_flow_warp(const float* x, const float* flo, const float* mul_m
                             float* overlap, int B, int C, int H, int W, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(x && flo && out, SB_EINVAL, "sb_flow_warp: null pointer");
+  
   SB_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_flow_warp: negative size");
   SB_REQUIRE((long long)H * W < (1ll << 31), SB_EUNSUP, "sb_flow_warp: plane too large");
   SB_REQUIRE(!overlap || C == 6, SB_EINVAL, "sb_flow_warp: overlap output needs C == 6 (image | mask)");
   const long long total = (long long)B * H * W;
   if (total == 0 || C == 0) return SB_OK;
+  SB_REQUIRE(x && flo && out, SB_EINVAL, "sb_flow_warp: null pointer");
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   const long long max_blocks = (long long)kNumSMs * 8 * 16;

@@ -10,6 +10,11 @@
 //
 // HBM-bound: coordinates are computed, not loaded; per output pixel C planes
 // are gathered (4 taps) and C floats written: 2*C*4 algorithmic bytes / px.
+//
+// n_ones: the callers always warp cat(image, ones) (flowHomoAdpater.py:110-113,
+// :292,:310,:314) — the trailing all-ones planes are synthesised here
+// (((wa*1 + wb*1) + wc*1) + wd*1, the same fp32 sequence as sampling a stored
+// 1.0) instead of being materialised, concatenated and read back.
 #include "bilinear.cuh"
 
 namespace sb {
@@ -26,9 +31,10 @@ __global__ void __launch_bounds__(256)
 homo_warp_kernel(const float* __restrict__ U, const float* __restrict__ theta,
                  const float* __restrict__ xs, const float* __restrict__ ys,
                  float* __restrict__ out, int32_t* __restrict__ idx_dbg,
-                 int C_rt, int H, int W, int Hout, int Wout, int theta_batch,
+                 int C_rt, int n_ones, int H, int W, int Hout, int Wout, int theta_batch,
                  long long total /* B*Hout*Wout */) {
   const int C = (C_T > 0) ? C_T : C_rt;
+  const int Cout = C + n_ones;
   const long long oplane = (long long)Hout * Wout;
   const long long iplane = (long long)H * W;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
@@ -53,7 +59,12 @@ homo_warp_kernel(const float* __restrict__ U, const float* __restrict__ theta,
       d[0] = tap.x0; d[oplane] = tap.x1; d[2 * oplane] = tap.y0; d[3 * oplane] = tap.y1;
     }
     const float* src = U + b * C * iplane;
-    float* dst = out + b * C * oplane + rem;
+    float* dst = out + b * Cout * oplane + rem;
+    if (n_ones > 0) {
+      const float one = fadd(fadd(fadd(fmul(tap.wa, 1.0f), fmul(tap.wb, 1.0f)), fmul(tap.wc, 1.0f)),
+                             fmul(tap.wd, 1.0f));
+      for (int ch = 0; ch < n_ones; ++ch) stg_stream(dst + (C + ch) * oplane, one);
+    }
     if (C_T > 0) {
       float v[C_T > 0 ? C_T : 1];
 #pragma unroll
@@ -69,29 +80,31 @@ homo_warp_kernel(const float* __restrict__ U, const float* __restrict__ theta,
 }  // namespace sb
 
 extern "C" int sb_homo_warp(const float* U, const float* theta, const float* xs, const float* ys,
-                            float* out, int32_t* idx_dbg, int B, int C, int H, int W, int Hout,
-                            int Wout, int theta_batch, sb_stream_t stream) {
+                            float* out, int32_t* idx_dbg, int B, int C, int n_ones, int H, int W,
+                            int Hout, int Wout, int theta_batch, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(U && theta && xs && ys && out, SB_EINVAL, "sb_homo_warp: null pointer");
-  SB_REQUIRE(B >= 0 && C >= 0 && H > 0 && W > 0 && Hout >= 0 && Wout >= 0, SB_EINVAL,
+  
+  SB_REQUIRE(B >= 0 && C >= 0 && n_ones >= 0 && H > 0 && W > 0 && Hout >= 0 && Wout >= 0, SB_EINVAL,
              "sb_homo_warp: bad size");
   SB_REQUIRE(theta_batch == 1 || theta_batch == B, SB_EINVAL,
              "sb_homo_warp: theta batch %d must be 1 or B=%d", theta_batch, B);
   SB_REQUIRE((long long)H * W < (1ll << 31) && (long long)Hout * Wout < (1ll << 31), SB_EUNSUP,
              "sb_homo_warp: plane too large");
   const long long total = (long long)B * Hout * Wout;
-  if (total == 0 || C == 0) return SB_OK;
+  if (total == 0 || C + n_ones == 0) return SB_OK;
+  SB_REQUIRE((U || C == 0) && theta && xs && ys && out, SB_EINVAL, "sb_homo_warp: null pointer");
   const int threads = 256;
   long long blocks = (total + threads - 1) / threads;
   const long long max_blocks = (long long)kNumSMs * 8 * 16;
   if (blocks > max_blocks) blocks = max_blocks;
   cudaStream_t s = as_stream(stream);
 #define SB_HOMO_LAUNCH(CT)                                                                    \
-  homo_warp_kernel<CT><<<(int)blocks, threads, 0, s>>>(U, theta, xs, ys, out, idx_dbg, C, H, \
-                                                       W, Hout, Wout, theta_batch, total)
+  homo_warp_kernel<CT><<<(int)blocks, threads, 0, s>>>(U, theta, xs, ys, out, idx_dbg, C, n_ones, \
+                                                       H, W, Hout, Wout, theta_batch, total)
   switch (C) {
     case 1: SB_HOMO_LAUNCH(1); break;
+    case 2: SB_HOMO_LAUNCH(2); break;
     case 3: SB_HOMO_LAUNCH(3); break;
     case 6: SB_HOMO_LAUNCH(6); break;
     default: SB_HOMO_LAUNCH(0); break;

@@ -148,13 +148,14 @@ extern "C" int sb_morph_open(const float* mask, float* out, int P, int H, int W,
                              int border_is_zero, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(mask && out, SB_EINVAL, "sb_morph_open: null pointer");
+  
   SB_REQUIRE(P >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_morph_open: bad size");
   SB_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1), SB_EUNSUP,
              "sb_morph_open: kernel %dx%d must be odd", kh, kw);
   SB_REQUIRE(kh <= kMorphMaxK && kw <= kMorphMaxK, SB_EUNSUP, "sb_morph_open: kernel %dx%d > %d", kh,
              kw, kMorphMaxK);
   if ((long long)P * H * W == 0) return SB_OK;
+  SB_REQUIRE(mask && out, SB_EINVAL, "sb_morph_open: null pointer");
   const int tiles_x = (W + kMorphOutW - 1) / kMorphOutW, tiles_y = (H + kMorphTY - 1) / kMorphTY;
   const long long tiles = (long long)P * tiles_x * tiles_y;
   SB_REQUIRE(tiles < (1ll << 31), SB_EUNSUP, "sb_morph_open: too many tiles");

@@ -77,12 +77,13 @@ extern "C" int sb_range_map(const float* flow, unsigned long long* accum, float*
                             int H, int W, int mode, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(flow && accum && range_map, SB_EINVAL, "sb_range_map: null pointer");
+  
   SB_REQUIRE(B >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_range_map: bad size");
   SB_REQUIRE(mode >= 0 && mode <= 3, SB_EINVAL, "sb_range_map: mode %d", mode);
   SB_REQUIRE((long long)H * W < (1ll << 31), SB_EUNSUP, "sb_range_map: plane too large");
   const long long total = (long long)B * H * W;
   if (total == 0) return SB_OK;
+  SB_REQUIRE(flow && accum && range_map, SB_EINVAL, "sb_range_map: null pointer");
   cudaStream_t s = as_stream(stream);
   SB_CUDA(cudaMemsetAsync(accum, 0, (size_t)total * sizeof(unsigned long long), s));
   long long blocks = (total + 255) / 256;

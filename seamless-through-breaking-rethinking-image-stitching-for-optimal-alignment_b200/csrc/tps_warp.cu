@@ -85,7 +85,7 @@ extern "C" int sb_tps_warp(const float* U, const float* T, const float* source, 
                            int W, int Hout, int Wout, int pn, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  SB_REQUIRE(U && T && source && xs && ys && out, SB_EINVAL, "sb_tps_warp: null pointer");
+  
   SB_REQUIRE(B >= 0 && C >= 0 && H > 0 && W > 0 && Hout >= 0 && Wout >= 0 && pn >= 0, SB_EINVAL,
              "sb_tps_warp: bad size");
   SB_REQUIRE(pn <= kTpsMaxPn, SB_EUNSUP, "sb_tps_warp: pn=%d > %d control points", pn, kTpsMaxPn);
@@ -93,6 +93,7 @@ extern "C" int sb_tps_warp(const float* U, const float* T, const float* source, 
              "sb_tps_warp: plane too large");
   const long long oplane = (long long)Hout * Wout;
   if ((long long)B * oplane == 0 || C == 0) return SB_OK;
+  SB_REQUIRE(U && T && source && xs && ys && out, SB_EINVAL, "sb_tps_warp: null pointer");
   const int threads = 256;
   long long bpi = (oplane + threads - 1) / threads;
   const long long cap = (long long)kNumSMs * 8 * 4 / (B > 0 ? B : 1) + 1;

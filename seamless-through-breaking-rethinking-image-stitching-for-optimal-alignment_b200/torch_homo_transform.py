@@ -29,12 +29,15 @@ def _as_int(v) -> int:
     return int(v.item()) if isinstance(v, torch.Tensor) else int(v)
 
 
-def transformer(U, theta, out_size, return_indices=False, **kwargs):
+def transformer(U, theta, out_size, return_indices=False, append_ones=0, **kwargs):
     """U ``[B,C,H,W]``, theta ``[B or 1,3,3]`` (normalised [-1,1] coordinates),
     ``out_size=(Hout,Wout)`` ints or 0-dim tensors -> ``[B,C,Hout,Wout]``.
 
     ``return_indices=True`` (extension for the parity tests) also returns the
-    clamped integer grid indices ``[B,4,Hout,Wout]`` int32 = (x0,x1,y0,y1)."""
+    clamped integer grid indices ``[B,4,Hout,Wout]`` int32 = (x0,x1,y0,y1).
+    ``append_ones=n`` (extension) behaves exactly like
+    ``transformer(torch.cat((U, ones[:, :n]), 1), ...)`` — what every call site of the
+    reference does — without materialising or reading the ones planes."""
     lib = _lib.load()
     u = _lib.dev_f32(U, "U")
     if u.dim() != 4:
@@ -45,9 +48,10 @@ def transformer(U, theta, out_size, return_indices=False, **kwargs):
         raise ValueError(f"transformer: theta batch {th.shape[0]} incompatible with B={b}")
     hout, wout = _as_int(out_size[0]), _as_int(out_size[1])
     xs, ys = linspace_table(wout, u.device), linspace_table(hout, u.device)
-    out = torch.empty((b, c, hout, wout), dtype=torch.float32, device=u.device)
+    n1 = int(append_ones)
+    out = torch.empty((b, c + n1, hout, wout), dtype=torch.float32, device=u.device)
     idx = torch.empty((b, 4, hout, wout), dtype=torch.int32, device=u.device) if return_indices else None
     _lib.check(lib.sb_homo_warp(_lib.ptr(u), _lib.ptr(th), _lib.ptr(xs), _lib.ptr(ys), _lib.ptr(out),
-                                _lib.ptr(idx), b, c, h, w, hout, wout, th.shape[0], _lib.stream_ptr()),
+                                _lib.ptr(idx), b, c, n1, h, w, hout, wout, th.shape[0], _lib.stream_ptr()),
                "sb_homo_warp")
     return (out, idx) if return_indices else out

@@ -118,7 +118,6 @@ def _range_map(flow, mode):
     accum = torch.empty((b, h, w), dtype=torch.int64, device=fl.device)
     _lib.check(lib.sb_range_map(_lib.ptr(fl), _lib.ptr(accum), _lib.ptr(out), b, h, w, mode,
                                 _lib.stream_ptr()), "sb_range_map")
-    accum.record_stream(torch.cuda.current_stream())
     return out
 
 

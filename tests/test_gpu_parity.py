@@ -520,3 +520,50 @@ def test_hot_path_step_small(sb):
                              return_overlap=True)
     assert_bits_equal(host(out["final_warp_output"]), ref_fw, "final_warp_output")
     assert_bits_equal(host(out["overlap"]), ref_ov, "overlap")
+
+
+# ===================================================================== G1 fused geometry / ones fusion
+def test_homo_append_ones_equals_cat(sb):
+    c = cases.homo_small()
+    U3 = cu(c["U"][:, :3].contiguous())
+    full, idx = sb.torch_homo_transform.transformer(torch.cat((U3, torch.ones_like(U3)), 1), cu(c["theta"]), c["out_size"],
+                                                    return_indices=True)
+    fused, idx2 = sb.torch_homo_transform.transformer(U3, cu(c["theta"]), c["out_size"], return_indices=True, append_ones=3)
+    assert torch.equal(full, fused) and torch.equal(idx, idx2)
+    g = golden("homo_small")     # the golden case IS cat(image, ones)
+    assert_bits_equal(host(fused), g["out"], "append_ones vs reference golden")
+    f2 = sb.torch_homo_transform.transformer(cu(c["U"][:, :2].contiguous()), cu(c["theta"]), c["out_size"], append_ones=1)
+    assert torch.equal(f2, full[:, [0, 1, 3]])
+
+
+def test_dlt_theta_vs_oracle(sb):
+    g = golden("geometry")
+    src = torch.tensor([[0.0, 0.0], [64, 0.0], [0.0, 48], [64, 48]]).unsqueeze(0).repeat(3, 1, 1)
+    dst = torch.from_numpy(g["dst"])
+    H = host(sb.torch_DLT.tensor_DLT(cu(src), cu(dst)))
+    assert max_abs(H, g["H"]) <= 1e-4                      # reference: fp32 LU; here fp64 elimination, one rounding
+    M = sb.torch_DLT.norm_matrix(64, 48)
+    Hh, th, thi = sb.torch_DLT.dlt_thetas(cu(src), cu(dst), left=sb.torch_DLT._inv3(M), right=M)
+    Mn = np.array(M, np.float64).reshape(3, 3)
+    want = np.linalg.inv(Mn) @ g["H"].astype(np.float64) @ Mn
+    want_i = np.linalg.inv(Mn) @ np.linalg.inv(g["H"].astype(np.float64)) @ Mn
+    assert max_abs(host(th), want) <= 1e-4 * np.abs(want).max()
+    assert max_abs(host(thi), want_i) <= 1e-4 * np.abs(want_i).max()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sb.torch_DLT.tensor_DLT(src, dst)
+
+
+def test_step_graph_replay_matches_eager(sb):
+    """The whole step is sync-free and capturable; a replay reproduces the eager outputs bit-for-bit."""
+    from stitch_b200.pipeline import HotPath, make_pair_batch
+    pb = make_pair_batch(0, 2, size=128, iters=2).map(lambda t: t.cuda())
+    hp = HotPath(size=128, iters=2, pyramid=True)
+    eager = hp.step(pb)
+    keep = {k: eager[k].clone() for k in ("final_warp_output", "overlap", "origin_occlusion_mask", "cost_volume", "output_H_inv")}
+    tok = eager["cost_tokens"][3].clone()
+    hp.capture(pb)
+    out = hp.replay()
+    torch.cuda.synchronize()
+    for k, v in keep.items():
+        assert torch.equal(out[k], v), k
+    assert torch.equal(out["cost_tokens"][3], tok)

@@ -1,0 +1,93 @@
+"""Per-kernel device timings at BASELINE config-2 size (B=16, 512^2), CUDA events,
+inputs larger than L2 or rotated so nothing is re-served from L2. Prints achieved
+algorithmic GB/s against MEASURED_PEAKS.json."""
+import json, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import stitch_b200 as sb
+from stitch_b200 import corr as C
+
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timeit(fn, n=20, warm=3):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def report(name, ms, nbytes):
+    gbs = nbytes / ms / 1e6
+    print(f"{name:34s} {ms*1e3:9.1f} us  {nbytes/1e6:9.1f} MB  {gbs:8.0f} GB/s  {100*gbs/PEAK:5.1f}% of HBM peak", flush=True)
+
+
+def main():
+    B, S = 16, 512
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    # ---- corr
+    f1, f2 = rnd(B, 256, 64, 64), rnd(B, 256, 64, 64)
+    report("feat_to_tokens_bf16", timeit(lambda: C.tokens_bf16(f1)), B * 4096 * 256 * 6)
+    t1, t2 = C.tokens_bf16(f1), C.tokens_bf16(f2)
+    n = 4096
+    for lv in (0, 3):
+        ms = timeit(lambda: C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_levels=lv))
+        byt = B * (n * n * 4 * (1 + (0.328125 if lv else 0)) + 2 * n * 256 * 2)
+        report(f"corr_umma (pyramid levels={lv})", ms, byt)
+        print(f"{'':34s} tensor: {B*2*n*n*256/ms/1e9:.0f} TFLOP/s")
+    # ---- lookup
+    vol = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64))
+    maps = vol.view(B * n, 1, 64, 64)
+    coords = sb.lookup.coords_grid(B, 64, 64, device="cuda") + rnd(B, 2, 64, 64) * 2
+    report("corr_lookup r=4", timeit(lambda: sb.encode_flow_token(maps, coords)), B * n * 732)
+    pyr = sb.corr_pyramid(f1, f2, 4)
+    report("corr_lookup pyramid (4 levels)", timeit(lambda: sb.encode_flow_token_pyramid(pyr, coords)), B * n * 2904)
+    del vol, maps, pyr
+    # ---- warps
+    img = torch.rand(B, 3, S, S, device="cuda", generator=g) * 255
+    x6 = torch.rand(B, 6, S, S, device="cuda", generator=g) * 255
+    lo = rnd(B, 2, 64, 64) * 2
+    flo = torch.nn.functional.interpolate(lo, size=(S, S), mode="bilinear", align_corners=True)
+    occ = (torch.rand(B, 1, S, S, device="cuda", generator=g) < 0.8).float()
+    px = B * S * S
+    report("flow_warp C=6", timeit(lambda: sb.warp(x6, flo)), px * 56)
+    report("flow_warp C=6 +mask +overlap", timeit(lambda: sb.warp(x6, flo, mul_mask=occ, return_overlap=True)), px * 64)
+    noise = rnd(B, 2, S, S) * 4
+    report("flow_warp C=6 (noise flow)", timeit(lambda: sb.warp(x6, noise)), px * 56)
+    src = sb.torch_DLT.corner_points(S, S, B, "cuda")
+    M = sb.torch_DLT.norm_matrix(S / 8, S / 8)
+    H, th, thi = sb.torch_DLT.dlt_thetas(src / 8, (src + rnd(B, 4, 2) * 20) / 8, left=sb.torch_DLT._inv3(M), right=M)
+    report("dlt_theta", timeit(lambda: sb.torch_DLT.dlt_thetas(src / 8, src / 8 + 1, left=sb.torch_DLT._inv3(M), right=M)), B * 200)
+    report("homo_warp C=6", timeit(lambda: sb.torch_homo_transform.transformer(x6, th, (S, S))), px * 48)
+    report("homo_warp C=3 + 3 ones", timeit(lambda: sb.torch_homo_transform.transformer(img, th, (S, S), append_ones=3)), px * 36)
+    report("range_map (occlusion, thresholded)", timeit(lambda: sb.compute_occlusion(flo, flo, "wang", occlusion_are_zeros=True, threshold=True)), px * 28)
+    report("morph_open 19x19", timeit(lambda: sb.preprocess_occlusion_mask(occ)), px * 8)
+    h1, h2, fw = x6, x6.flip(0), x6.flip(1)
+    report("composite_test_out", timeit(lambda: sb.composite_test_out(h1, h2, fw, occ)), px * 119)
+    net_out = torch.rand(B, 1, S, S, device="cuda", generator=g)
+    report("build_model", timeit(lambda: sb.build_model(lambda *a: net_out, img, img, img, img)), px * 88)
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, 13, device="cuda"), torch.linspace(-1, 1, 13, device="cuda"), indexing="ij")
+    sp = torch.stack([xs, ys], -1).reshape(1, -1, 2).repeat(B, 1, 1)
+    tg = sp + 0.02 * rnd(B, 169, 2)
+    T = sb.torch_tps_transform.solve_system(sp, tg)
+    lib = sb._lib.load()
+    xs_t, ys_t = sb.torch_homo_transform.linspace_table(S, x6.device), sb.torch_homo_transform.linspace_table(S, x6.device)
+    out = torch.empty_like(x6)
+    def tps_only():
+        sb._lib.check(lib.sb_tps_warp(sb._lib.ptr(x6), sb._lib.ptr(T), sb._lib.ptr(sp), sb._lib.ptr(xs_t), sb._lib.ptr(ys_t),
+                                      sb._lib.ptr(out), None, B, 6, S, S, S, S, 169, sb._lib.stream_ptr()), "tps")
+    ms = timeit(tps_only, n=5)
+    report("tps_warp pn=169 (kernel only)", ms, px * 48)
+    print(f"{'':34s} {px*169/ms/1e6:.1f} G basis evaluations/s")
+
+
+if __name__ == "__main__":
+    main()

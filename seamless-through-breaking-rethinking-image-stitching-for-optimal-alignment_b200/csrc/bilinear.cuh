@@ -58,8 +58,8 @@ struct UdisTap {
 
   // x, y: normalised sample position in [-1,1] (torch_homo_transform.py:29-30).
   __device__ __forceinline__ void setup(float xn, float yn, int H, int W) {
-    float x = fdiv(fmul(fadd(xn, 1.0f), (float)W), 2.0f);
-    float y = fdiv(fmul(fadd(yn, 1.0f), (float)H), 2.0f);
+    float x = fmul(fmul(fadd(xn, 1.0f), (float)W), 0.5f);   // * 0.5 == / 2.0 exactly
+    float y = fmul(fmul(fadd(yn, 1.0f), (float)H), 0.5f);
     // torch: floor(x).int() — saturate so that garbage coordinates (|x| huge,
     // NaN) still clamp into the image like the reference's int32 cast + clamp.
     float xf = floorf(x), yf = floorf(y);

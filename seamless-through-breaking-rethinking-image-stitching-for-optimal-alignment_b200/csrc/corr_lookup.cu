@@ -109,6 +109,133 @@ corr_lookup_kernel(const float* __restrict__ cost_maps, const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fast path: r = 4 (the only radius the reference uses), W2 % 4 == 0.
+// The generic kernel above is instruction-bound (~1000 issued instructions per
+// query: per-tap divisions, runtime index divisions, masks).  Here
+//   * the 9 x- and 9 y-coordinates of a query are round-tripped ONCE by lanes
+//     0..17 (the 81 taps are their outer product) and shared with shuffles;
+//   * the window is zero-filled in shared memory, which IS grid_sample's zeros
+//     padding (an out-of-range tap multiplies its weight by 0.0 in the same fma
+//     chain), so the taps need no masks;
+//   * lane l < 27 owns window row pair j = l % 9 and the three x-positions
+//     i = 3*(l/9) + {0,1,2}: 8 shared-memory loads feed 3 taps;
+//   * all index math is 32-bit and compile-time where possible.
+// A query whose taps do not fit the staged window (non-finite coordinates) is
+// handled by the generic per-tap gather.
+constexpr int kFastR = 4, kFastSide = 9;
+constexpr int kFastRows = 12, kFastPitch = 20;   // 12 x 16 floats, rows padded to 20 words
+constexpr int kFastQ = 4;                        // queries per warp, all loads issued up front
+
+// grid = (ceil(HW1 / 32), B): a CTA owns 32 consecutive queries of one batch element,
+// warp w the 4 queries [4w, 4w+4) — no index divisions, and 4 x (1 + 2) independent
+// global loads in flight per warp hide the two dependent DRAM round trips.
+__global__ void __launch_bounds__(kLookupWarps * 32)
+corr_lookup_r4_kernel(const float* __restrict__ cost_maps, const float* __restrict__ coords,
+                      float* __restrict__ out, int HW1, int H2, int W2, float coord_scale,
+                      int out_stride, int out_offset) {
+  __shared__ __align__(16) float s_win[kLookupWarps][kFastQ][kFastRows * kFastPitch];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int pos0 = blockIdx.x * (kLookupWarps * kFastQ) + warp * kFastQ;
+  if (pos0 >= HW1) return;
+  const float denx = (float)(W2 - 1), deny = (float)(H2 - 1);
+  const float halfx = fmul((float)(W2 - 1), 0.5f), halfy = fmul((float)(H2 - 1), 0.5f);  // == /2 exactly
+  const int map_sz = H2 * W2;
+  // lane roles
+  const bool is_x = lane < kFastSide;
+  const int cidx = is_x ? lane : (lane < 2 * kFastSide ? lane - kFastSide : 0);
+  const float cden = is_x ? denx : deny, chalf = is_x ? halfx : halfy;
+  const float coff = (float)(cidx - kFastR);
+  const int tj = lane % kFastSide, tig = (lane / kFastSide) % 3;   // tap row / x-group (lanes >= 27 idle)
+  const int wrow0 = lane >> 2, wch = lane & 3;                     // window chunk owned in pass 0
+  const float* cbase = coords + ((size_t)b * 2 + (is_x ? 0 : 1)) * HW1 + pos0;
+  const size_t q0 = (size_t)b * HW1 + pos0;
+
+  // ---- phase A: the 4 centre coordinates (independent loads)
+  float c_raw[kFastQ];
+#pragma unroll
+  for (int k = 0; k < kFastQ; ++k) c_raw[k] = (pos0 + k < HW1) ? __ldg(cbase + k) : 0.0f;
+
+  // ---- phase B: per-axis round trips, window origins, window loads (8 x LDG.128 in flight)
+  int fi[kFastQ], wy0[kFastQ], ax[kFastQ];
+  float wfrac[kFastQ];
+  float4 v0[kFastQ], v1[kFastQ];
+#pragma unroll
+  for (int k = 0; k < kFastQ; ++k) {
+    const float t = grid_roundtrip(fadd(fmul(c_raw[k], coord_scale), coff), cden, chalf);
+    const float fl = floorf(t);
+    wfrac[k] = fsub(t, fl);
+    fi[k] = sat_floor_to_int(fl, -100000, 100000);
+    const int x0i = __shfl_sync(0xffffffffu, fi[k], 0), y0i = __shfl_sync(0xffffffffu, fi[k], kFastSide);
+    wy0[k] = y0i - 1;
+    ax[k] = (x0i - 1) & ~3;
+    const float* map = cost_maps + (q0 + k) * map_sz;
+    const int gx = ax[k] + wch * 4;
+    const bool xin = (gx >= 0) & (gx + 3 < W2) & (pos0 + k < HW1);
+    const int gy = wy0[k] + wrow0;
+    v0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    v1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xin & (gy >= 0) & (gy < H2)) v0[k] = ldg_stream4(map + gy * W2 + gx);
+    if (xin & (lane < 16) & (gy + 8 >= 0) & (gy + 8 < H2)) v1[k] = ldg_stream4(map + (gy + 8) * W2 + gx);
+  }
+#pragma unroll
+  for (int k = 0; k < kFastQ; ++k) {
+    float* win = s_win[warp][k];
+    *reinterpret_cast<float4*>(win + wrow0 * kFastPitch + wch * 4) = v0[k];
+    if (lane < 16) *reinterpret_cast<float4*>(win + (wrow0 + 8) * kFastPitch + wch * 4) = v1[k];
+  }
+  __syncwarp();
+
+  // ---- phase C: taps
+#pragma unroll
+  for (int k = 0; k < kFastQ; ++k) {
+    if (pos0 + k >= HW1) break;                                    // warp-uniform
+    const float* win = s_win[warp][k];
+    const int yn = __shfl_sync(0xffffffffu, fi[k], kFastSide + tj);
+    const float n = __shfl_sync(0xffffffffu, wfrac[k], kFastSide + tj);
+    int xw[3];
+    float wv[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      xw[m] = __shfl_sync(0xffffffffu, fi[k], 3 * tig + m);
+      wv[m] = __shfl_sync(0xffffffffu, wfrac[k], 3 * tig + m);
+    }
+    const int ly = yn - wy0[k];
+    bool fits = (ly >= 0) & (ly + 1 < kFastRows);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) fits &= (xw[m] - ax[k] >= 0) & (xw[m] - ax[k] + 1 < 16);
+    const bool all_fit = __all_sync(0xffffffffu, fits | (lane >= 27));
+    float* orow = out + (q0 + k) * out_stride + out_offset;
+    if (all_fit) {
+      if (lane < 27) {
+        const float s = fsub(1.0f, n);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          const float w = wv[m], e = fsub(1.0f, w);
+          const float* wp = win + ly * kFastPitch + (xw[m] - ax[k]);
+          const float v_nw = wp[0], v_ne = wp[1], v_sw = wp[kFastPitch], v_se = wp[kFastPitch + 1];
+          const float nw = fmul(s, e), ne = fmul(s, w), sw = fmul(n, e), se = fmul(n, w);
+          orow[(3 * tig + m) * kFastSide + tj] =
+              __fmaf_rn(v_se, se, __fmaf_rn(v_sw, sw, __fmaf_rn(v_ne, ne, fmul(v_nw, nw))));
+        }
+      }
+    } else {
+      // cold path (non-finite coordinates): per-tap masked gather straight from global memory
+      const float* cb = coords + (size_t)b * 2 * HW1 + pos0 + k;
+      const float cx = fmul(__ldg(cb), coord_scale), cy = fmul(__ldg(cb + HW1), coord_scale);
+      const float* map = cost_maps + (q0 + k) * map_sz;
+      for (int t = lane; t < kFastSide * kFastSide; t += 32) {
+        const int i = t / kFastSide, j = t - i * kFastSide;
+        GridTap tap;
+        tap.setup(grid_roundtrip(fadd(cx, (float)(i - kFastR)), denx, halfx),
+                  grid_roundtrip(fadd(cy, (float)(j - kFastR)), deny, halfy), H2, W2);
+        orow[t] = tap.sample(map, W2);
+      }
+    }
+  }
+}
+
 // Generic bilinear_sampler: one thread per output location, loops channels.
 __global__ void __launch_bounds__(256)
 bilinear_sampler_kernel(const float* __restrict__ img, const float* __restrict__ coords,
@@ -150,6 +277,14 @@ extern "C" int sb_corr_lookup(const float* cost_maps, const float* coords, float
   long long blocks = (nq + kLookupWarps - 1) / kLookupWarps;
   const long long max_blocks = (long long)kNumSMs * 8 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
+  if (r == kFastR && (W2 & 3) == 0 && B <= 65535) {
+    const int hw1 = H1 * W1, per_cta = kLookupWarps * kFastQ;
+    dim3 grid((hw1 + per_cta - 1) / per_cta, B);
+    corr_lookup_r4_kernel<<<grid, kLookupWarps * 32, 0, as_stream(stream)>>>(
+        cost_maps, coords, out, hw1, H2, W2, coord_scale, out_stride, out_offset);
+    SB_LAUNCH_CHECK("corr_lookup_r4_kernel");
+    return SB_OK;
+  }
   corr_lookup_kernel<<<(int)blocks, kLookupWarps * 32, 0, as_stream(stream)>>>(
       cost_maps, coords, out, nq, H1 * W1, H2, W2, r, coord_scale, out_stride, out_offset);
   SB_LAUNCH_CHECK("corr_lookup_kernel");

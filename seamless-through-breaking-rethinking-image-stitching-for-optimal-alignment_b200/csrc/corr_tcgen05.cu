@@ -111,7 +111,8 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN 
 template <bool POOL>
 __global__ void __launch_bounds__(256, 1)
 corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_v, const CorrParams p) {
+                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_l1,
+                 const CorrParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -134,6 +135,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_b);
     ptx::prefetch_tensormap(&map_v);
+    if (POOL) ptx::prefetch_tensormap(&map_l1);
   }
   if (warp == 1 && lane == 0) {
     ptx::mbar_init(bar_a_full, 1);
@@ -293,11 +295,26 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
 
         if (POOL) {
-          if (p.lvl1 && row_ok) {
-            float* o = p.lvl1 + (q * p.H2h + t) * 32;
+          if (p.lvl1) {
+            // level 1 of this tile = 32 rows x 32 floats per warp: same swizzled staging +
+            // TMA store as a volume slice (full 128-byte lines instead of 32 scattered rows)
+            if (lane == 0) ptx::tma_store_wait_read<1>();
+            __syncwarp();
+            const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              stg_stream4(o + 4 * c, make_float4(h1[4 * c], h1[4 * c + 1], h1[4 * c + 2], h1[4 * c + 3]));
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t a = dst + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(h1[4 * c]),
+                           "f"(h1[4 * c + 1]), "f"(h1[4 * c + 2]), "f"(h1[4 * c + 3])
+                           : "memory");
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_3d(&map_l1, my_stage + sbuf * kStageBufBytes, t * 32, mb * BM + wq * 32, b);
+              ptx::tma_store_commit();
+            }
+            sbuf ^= 1;
           }
           // level 2: pool level-1 rows (t even, t odd)
           if ((tt & 1) == 0) {
@@ -478,7 +495,7 @@ extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, fl
   cudaStream_t s = as_stream(stream);
   const int Cpad = round_up(C, 64);
 
-  CUtensorMap map_a, map_b, map_v;
+  CUtensorMap map_a, map_b, map_v, map_l1;
   int rc;
   rc = make_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok1, Cpad, N1, B, BKP, BM, "A");
   if (rc) return rc;
@@ -486,6 +503,14 @@ extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, fl
   if (rc) return rc;
   rc = make_map_3d(&map_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, vol, N2, N1, B, 32, 32, "V");
   if (rc) return rc;
+  map_l1 = map_v;
+  if (fused_pool && lvl1) {
+    // lvl1 [B*N1, H2/2, 32] viewed as rows of (H2/2)*32 floats: tile t owns columns [32t, 32t+32)
+    SB_REQUIRE(aligned16(lvl1), SB_EINVAL, "sb_corr_tokens: lvl1 must be 16-byte aligned");
+    rc = make_map_3d(&map_l1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl1, (unsigned long long)(H2 / 2) * 32, N1, B,
+                     32, 32, "L1");
+    if (rc) return rc;
+  }
 
   if (!g_dbg) {
     SB_CUDA(cudaHostAlloc(&g_dbg_host, 64, cudaHostAllocMapped));
@@ -513,9 +538,9 @@ extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, fl
     attr_set = true;
   }
   if (fused_pool)
-    corr_umma_kernel<true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, p);
+    corr_umma_kernel<true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, p);
   else
-    corr_umma_kernel<false><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, p);
+    corr_umma_kernel<false><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, p);
   SB_LAUNCH_CHECK("corr_umma_kernel");
 
   if (want_pool && !fused_pool) {

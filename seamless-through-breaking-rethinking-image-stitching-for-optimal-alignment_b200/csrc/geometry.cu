@@ -36,34 +36,37 @@ __global__ void dlt_theta_kernel(const float* __restrict__ src_p, const float* _
                                  float* __restrict__ theta, float* __restrict__ theta_inv, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  // A h = rhs, rows alternate (x y 1 0 0 0 -x*x' -y*x') / (0 0 0 x y 1 -x*y' -y*y')  (torch_DLT.py:8-15)
-  double A[8][9];
-  for (int k = 0; k < 4; ++k) {
-    const double x = src_p[(b * 4 + k) * 2], y = src_p[(b * 4 + k) * 2 + 1];
-    const double u = dst_p[(b * 4 + k) * 2], v = dst_p[(b * 4 + k) * 2 + 1];
-    double* r0 = A[2 * k];
-    double* r1 = A[2 * k + 1];
-    r0[0] = x; r0[1] = y; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -u * x; r0[7] = -u * y; r0[8] = u;
-    r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = x; r1[4] = y; r1[5] = 1; r1[6] = -v * x; r1[7] = -v * y; r1[8] = v;
-  }
-  for (int c = 0; c < 8; ++c) {            // Gaussian elimination, partial pivoting
-    int piv = c;
-    double best = fabs(A[c][c]);
-    for (int r = c + 1; r < 8; ++r)
-      if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); piv = r; }
-    if (piv != c)
-      for (int k = c; k < 9; ++k) { const double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
-    const double inv = 1.0 / A[c][c];
-    for (int r = c + 1; r < 8; ++r) {
-      const double f = A[r][c] * inv;
-      for (int k = c; k < 9; ++k) A[r][k] -= f * A[c][k];
+  // Four correspondences in general position determine H up to scale, so the 8x8 DLT system
+  // (torch_DLT.py:8-15, h33 = 1) has the closed-form solution H = Q(dst) * Q(src)^-1 / [.]_33,
+  // where Q(p) is the projective map of the unit square onto the quad p (Heckbert 1989).
+  // ~150 fp64 flops instead of a serial 8x8 elimination.
+  double qs[9], qd[9];
+  {
+    const float* pts[2] = {src_p + b * 8, dst_p + b * 8};
+    double* qq[2] = {qs, qd};
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      // point order of the reference: p0 = (0,0), p1 = (1,0), p2 = (0,1), p3 = (1,1) of the square
+      const double x0 = pts[w][0], y0 = pts[w][1], x1 = pts[w][2], y1 = pts[w][3];
+      const double x3 = pts[w][4], y3 = pts[w][5], x2 = pts[w][6], y2 = pts[w][7];
+      const double dx1 = x1 - x2, dx2 = x3 - x2, sx = x0 - x1 + x2 - x3;
+      const double dy1 = y1 - y2, dy2 = y3 - y2, sy = y0 - y1 + y2 - y3;
+      const double den = dx1 * dy2 - dx2 * dy1;
+      const double g = (sx * dy2 - dx2 * sy) / den;
+      const double hh = (dx1 * sy - sx * dy1) / den;
+      double* q = qq[w];
+      q[0] = x1 - x0 + g * x1; q[1] = x3 - x0 + hh * x3; q[2] = x0;
+      q[3] = y1 - y0 + g * y1; q[4] = y3 - y0 + hh * y3; q[5] = y0;
+      q[6] = g;                q[7] = hh;                q[8] = 1.0;
     }
   }
-  double h[9];
-  for (int r = 7; r >= 0; --r) {
-    double acc = A[r][8];
-    for (int k = r + 1; k < 8; ++k) acc -= A[r][k] * h[k];
-    h[r] = acc / A[r][r];
+  double qsi[9], h[9];
+  inv3(qs, qsi);
+  mul3(qd, qsi, h);
+  {
+    const double n = 1.0 / h[8];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) h[i] *= n;
   }
   h[8] = 1.0;
   // the reference rounds H to fp32 before using it further

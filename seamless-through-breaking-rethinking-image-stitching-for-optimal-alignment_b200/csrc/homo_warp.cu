@@ -15,6 +15,8 @@
 // :292,:310,:314) — the trailing all-ones planes are synthesised here
 // (((wa*1 + wb*1) + wc*1) + wd*1, the same fp32 sequence as sampling a stored
 // 1.0) instead of being materialised, concatenated and read back.
+//
+// Launch shape: grid (Wout/32, Hout/8, B), block (32, 8) — no index divisions.
 #include "bilinear.cuh"
 
 namespace sb {
@@ -31,49 +33,46 @@ __global__ void __launch_bounds__(256)
 homo_warp_kernel(const float* __restrict__ U, const float* __restrict__ theta,
                  const float* __restrict__ xs, const float* __restrict__ ys,
                  float* __restrict__ out, int32_t* __restrict__ idx_dbg,
-                 int C_rt, int n_ones, int H, int W, int Hout, int Wout, int theta_batch,
-                 long long total /* B*Hout*Wout */) {
+                 int C_rt, int n_ones, int H, int W, int Hout, int Wout, int theta_batch) {
   const int C = (C_T > 0) ? C_T : C_rt;
   const int Cout = C + n_ones;
-  const long long oplane = (long long)Hout * Wout;
-  const long long iplane = (long long)H * W;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
-       p += (long long)gridDim.x * blockDim.x) {
-    const long long b = p / oplane;
-    const long long rem = p - b * oplane;
-    const int r = (int)(rem / Wout), c = (int)(rem - (long long)r * Wout);
-    const float* th = theta + (theta_batch > 1 ? b * 9 : 0);
-    float t[9];
+  const int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
+  if (c >= Wout || r >= Hout) return;
+  const int b = blockIdx.z;
+  const int oplane = Hout * Wout, iplane = H * W;
+  const int rem = r * Wout + c;
+  const float* th = theta + (theta_batch > 1 ? b * 9 : 0);
+  float t[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) t[i] = __ldg(th + i);
-    const float gx = __ldg(xs + c), gy = __ldg(ys + r);
-    const float X = dot3(t, gx, gy), Y = dot3(t + 3, gx, gy);
-    float T = dot3(t + 6, gx, gy);
-    // smallers = 1e-6 * (1 - float(|t| >= 1e-7)); t = t + smallers   (:133-137)
-    const float ge = (fabsf(T) >= 1e-7f) ? 1.0f : 0.0f;
-    T = fadd(T, fmul(1e-6f, fsub(1.0f, ge)));
-    UdisTap tap;
-    tap.setup(fdiv(X, T), fdiv(Y, T), H, W);
-    if (idx_dbg) {
-      int32_t* d = idx_dbg + b * 4 * oplane + rem;
-      d[0] = tap.x0; d[oplane] = tap.x1; d[2 * oplane] = tap.y0; d[3 * oplane] = tap.y1;
-    }
-    const float* src = U + b * C * iplane;
-    float* dst = out + b * Cout * oplane + rem;
-    if (n_ones > 0) {
-      const float one = fadd(fadd(fadd(fmul(tap.wa, 1.0f), fmul(tap.wb, 1.0f)), fmul(tap.wc, 1.0f)),
-                             fmul(tap.wd, 1.0f));
-      for (int ch = 0; ch < n_ones; ++ch) stg_stream(dst + (C + ch) * oplane, one);
-    }
-    if (C_T > 0) {
-      float v[C_T > 0 ? C_T : 1];
+  for (int i = 0; i < 9; ++i) t[i] = __ldg(th + i);
+  const float gx = __ldg(xs + c), gy = __ldg(ys + r);
+  const float X = dot3(t, gx, gy), Y = dot3(t + 3, gx, gy);
+  float T = dot3(t + 6, gx, gy);
+  // smallers = 1e-6 * (1 - float(|t| >= 1e-7)); t = t + smallers   (:133-137)
+  const float ge = (fabsf(T) >= 1e-7f) ? 1.0f : 0.0f;
+  T = fadd(T, fmul(1e-6f, fsub(1.0f, ge)));
+  UdisTap tap;
+  tap.setup(fdiv(X, T), fdiv(Y, T), H, W);
+  if (idx_dbg) {
+    int32_t* d = idx_dbg + (size_t)b * 4 * oplane + rem;
+    d[0] = tap.x0; d[oplane] = tap.x1; d[2 * (size_t)oplane] = tap.y0; d[3 * (size_t)oplane] = tap.y1;
+  }
+  const float* src = U + (size_t)b * C * iplane;
+  float* dst = out + (size_t)b * Cout * oplane + rem;
+  if (n_ones > 0) {
+    const float one = fadd(fadd(fadd(fmul(tap.wa, 1.0f), fmul(tap.wb, 1.0f)), fmul(tap.wc, 1.0f)),
+                           fmul(tap.wd, 1.0f));
+    for (int ch = 0; ch < n_ones; ++ch) stg_stream(dst + (size_t)(C + ch) * oplane, one);
+  }
+  if (C_T > 0) {
+    float v[C_T > 0 ? C_T : 1];
 #pragma unroll
-      for (int ch = 0; ch < C_T; ++ch) v[ch] = tap.sample(src + ch * iplane, W);
+    for (int ch = 0; ch < C_T; ++ch) v[ch] = tap.sample(src + (size_t)ch * iplane, W);
 #pragma unroll
-      for (int ch = 0; ch < C_T; ++ch) stg_stream(dst + ch * oplane, v[ch]);
-    } else {
-      for (int ch = 0; ch < C; ++ch) stg_stream(dst + ch * oplane, tap.sample(src + ch * iplane, W));
-    }
+    for (int ch = 0; ch < C_T; ++ch) stg_stream(dst + (size_t)ch * oplane, v[ch]);
+  } else {
+    for (int ch = 0; ch < C; ++ch)
+      stg_stream(dst + (size_t)ch * oplane, tap.sample(src + (size_t)ch * iplane, W));
   }
 }
 
@@ -84,7 +83,6 @@ extern "C" int sb_homo_warp(const float* U, const float* theta, const float* xs,
                             int Hout, int Wout, int theta_batch, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  
   SB_REQUIRE(B >= 0 && C >= 0 && n_ones >= 0 && H > 0 && W > 0 && Hout >= 0 && Wout >= 0, SB_EINVAL,
              "sb_homo_warp: bad size");
   SB_REQUIRE(theta_batch == 1 || theta_batch == B, SB_EINVAL,
@@ -94,14 +92,12 @@ extern "C" int sb_homo_warp(const float* U, const float* theta, const float* xs,
   const long long total = (long long)B * Hout * Wout;
   if (total == 0 || C + n_ones == 0) return SB_OK;
   SB_REQUIRE((U || C == 0) && theta && xs && ys && out, SB_EINVAL, "sb_homo_warp: null pointer");
-  const int threads = 256;
-  long long blocks = (total + threads - 1) / threads;
-  const long long max_blocks = (long long)kNumSMs * 8 * 16;
-  if (blocks > max_blocks) blocks = max_blocks;
+  SB_REQUIRE(B <= 65535 && (Hout + 7) / 8 <= 65535, SB_EUNSUP, "sb_homo_warp: B or Hout too large for one launch");
+  const dim3 block(32, 8), grid((Wout + 31) / 32, (Hout + 7) / 8, B);
   cudaStream_t s = as_stream(stream);
-#define SB_HOMO_LAUNCH(CT)                                                                    \
-  homo_warp_kernel<CT><<<(int)blocks, threads, 0, s>>>(U, theta, xs, ys, out, idx_dbg, C, n_ones, \
-                                                       H, W, Hout, Wout, theta_batch, total)
+#define SB_HOMO_LAUNCH(CT)                                                                      \
+  homo_warp_kernel<CT><<<grid, block, 0, s>>>(U, theta, xs, ys, out, idx_dbg, C, n_ones, H, W, \
+                                              Hout, Wout, theta_batch)
   switch (C) {
     case 1: SB_HOMO_LAUNCH(1); break;
     case 2: SB_HOMO_LAUNCH(2); break;

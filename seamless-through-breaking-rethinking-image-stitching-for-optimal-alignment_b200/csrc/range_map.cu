@@ -18,35 +18,34 @@ namespace sb {
 
 __global__ void __launch_bounds__(256)
 range_splat_kernel(const float* __restrict__ flow, unsigned long long* __restrict__ accum, int H,
-                   int W, long long total) {
-  const long long plane = (long long)H * W;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
-       p += (long long)gridDim.x * blockDim.x) {
-    const long long b = p / plane, rem = p - b * plane;
-    const int py = (int)(rem / W), px = (int)(rem - (long long)py * W);
-    const float* fl = flow + b * 2 * plane + rem;
-    // coords = grid + flow (flow_to_warp, :54-69)
-    const float cx = fadd((float)px, ldg_stream(fl));
-    const float cy = fadd((float)py, ldg_stream(fl + plane));
-    const float fx = floorf(cx), fy = floorf(cy);
-    const float ox = fsub(cx, fx), oy = fsub(cy, fy);        // coords_offset (:121)
-    if (!(fx >= -1.0f && fx <= (float)W && fy >= -1.0f && fy <= (float)H)) continue;  // also NaN
-    const int ix = (int)fx, iy = (int)fy;
-    unsigned long long* acc = accum + b * plane;
+                   int W) {
+  // grid (W/32, H/8, B), block (32, 8): no index divisions
+  const int px = blockIdx.x * 32 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
+  if (px >= W || py >= H) return;
+  const int plane = H * W;
+  const size_t boff = (size_t)blockIdx.z * plane;
+  const float* fl = flow + 2 * boff + py * W + px;
+  // coords = grid + flow (flow_to_warp, :54-69)
+  const float cx = fadd((float)px, ldg_stream(fl));
+  const float cy = fadd((float)py, ldg_stream(fl + plane));
+  const float fx = floorf(cx), fy = floorf(cy);
+  const float ox = fsub(cx, fx), oy = fsub(cy, fy);        // coords_offset (:121)
+  if (!(fx >= -1.0f && fx <= (float)W && fy >= -1.0f && fy <= (float)H)) return;  // also NaN
+  const int ix = (int)fx, iy = (int)fy;
+  unsigned long long* acc = accum + boff;
 #pragma unroll
-    for (int di = 0; di < 2; ++di) {
+  for (int di = 0; di < 2; ++di) {
 #pragma unroll
-      for (int dj = 0; dj < 2; ++dj) {
-        const int tx = ix + di, ty = iy + dj;
-        if (tx < 0 || tx >= W || ty < 0 || ty >= H) continue;
-        // weights_i = (1 - di) - (-1)^di * off_x ; weights_j likewise (:158-160)
-        const float wi = di ? fsub(0.0f, fmul(-1.0f, ox)) : fsub(1.0f, ox);
-        const float wj = dj ? fsub(0.0f, fmul(-1.0f, oy)) : fsub(1.0f, oy);
-        const float w = fmul(wi, wj);
-        // w in [0, 1]: scale by 2^32 exactly (power of two), round to integer
-        const unsigned long long q = __float2ull_rn(w * 4294967296.0f);
-        if (q) atomicAdd(acc + (long long)ty * W + tx, q);
-      }
+    for (int dj = 0; dj < 2; ++dj) {
+      const int tx = ix + di, ty = iy + dj;
+      if (tx < 0 || tx >= W || ty < 0 || ty >= H) continue;
+      // weights_i = (1 - di) - (-1)^di * off_x ; weights_j likewise (:158-160)
+      const float wi = di ? fsub(0.0f, fmul(-1.0f, ox)) : fsub(1.0f, ox);
+      const float wj = dj ? fsub(0.0f, fmul(-1.0f, oy)) : fsub(1.0f, oy);
+      const float w = fmul(wi, wj);
+      // w in [0, 1]: scale by 2^32 exactly (power of two), round to integer
+      const unsigned long long q = __float2ull_rn(w * 4294967296.0f);
+      if (q) atomicAdd(acc + ty * W + tx, q);
     }
   }
 }
@@ -89,7 +88,8 @@ extern "C" int sb_range_map(const float* flow, unsigned long long* accum, float*
   long long blocks = (total + 255) / 256;
   const long long max_blocks = (long long)kNumSMs * 8 * 16;
   if (blocks > max_blocks) blocks = max_blocks;
-  range_splat_kernel<<<(int)blocks, 256, 0, s>>>(flow, accum, H, W, total);
+  SB_REQUIRE(B <= 65535 && (H + 7) / 8 <= 65535, SB_EUNSUP, "sb_range_map: B or H too large for one launch");
+  range_splat_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, s>>>(flow, accum, H, W);
   SB_LAUNCH_CHECK("range_splat_kernel");
   range_finalize_kernel<<<(int)blocks, 256, 0, s>>>(accum, range_map, mode, total);
   SB_LAUNCH_CHECK("range_finalize_kernel");

@@ -22,7 +22,7 @@ import torch
 from . import corr as corr_mod
 from . import lookup, torch_DLT, torch_homo_transform, warp_utils
 
-__all__ = ["shard_range", "PairBatch", "make_pair_batch", "HotPath", "algorithmic_work"]
+__all__ = ["shard_range", "PairBatch", "make_pair_batch", "HotPath", "StreamedHotPath", "algorithmic_work"]
 
 BASE_SEED = 1234  # out.py:7-8 of the reference seeds with 1234
 
@@ -171,8 +171,10 @@ class HotPath:
             tokens.append(lookup.encode_flow_token(maps_b, pb.coords[iters + it], self.r))
         # ---- homography stage (flowHomoAdpater.py:92-113)
         src_p = torch_DLT.corner_points(size, size, b, dev)
-        M = torch_DLT.norm_matrix(size / 8, size / 8)
-        H, H_mat, H_inv_mat = torch_DLT.dlt_thetas(src_p / 8, (src_p + pb.h_motion) / 8, left=torch_DLT._inv3(M), right=M)
+        if getattr(self, "_M", None) is None:
+            self._M = torch_DLT.norm_matrix(size / 8, size / 8)
+            self._M_inv = torch_DLT._inv3(self._M)
+        H, H_mat, H_inv_mat = torch_DLT.dlt_thetas(src_p / 8, (src_p + pb.h_motion) / 8, left=self._M_inv, right=self._M)
         output_H = torch_homo_transform.transformer(pb.image2, H_mat, (size, size), append_ones=3)
         output_H_inv = torch_homo_transform.transformer(pb.image1, H_inv_mat, (size, size), append_ones=3)
         # ---- occlusion + flow warp (+ overlap, + multiply) (:170-182)
@@ -182,3 +184,80 @@ class HotPath:
         return dict(final_warp_output=final_warp, overlap=overlap, origin_occlusion_mask=occ,
                     output_H=output_H, output_H_inv=output_H_inv, cost_tokens=tokens,
                     cost_volume=vol_f, cost_volume_back=vol_b, cost_pyramid=pyr_f, cost_pyramid_back=pyr_b)
+
+
+class StreamedHotPath:
+    """End-to-end driver for HOST-resident batches: pinned host inputs -> device -> step ->
+    pinned host results, double-buffered over three streams so that the host->device copy
+    of batch i+1 and the device->host copy of batch i-1 overlap the kernels of batch i
+    (PCIe is full duplex; the step itself is a captured CUDA graph per buffer set).
+
+    This replaces the reference's ``nn.DataParallel`` scatter / ``.cpu()`` round trip
+    (``evaluate.py:43-53``) for the hot path.
+    """
+
+    RESULT_KEYS = ("final_warp_output", "overlap", "origin_occlusion_mask")
+
+    def __init__(self, template: PairBatch, size: int = 512, iters: int = 12, pyramid: bool = True,
+                 device=None, depth: int = 2):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.depth = depth
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.slots = []
+        for _ in range(depth):
+            hp = HotPath(size=size, iters=iters, pyramid=pyramid)
+            dev_in = template.map(lambda t: torch.empty_like(t, device=self.device))
+            for d, h in zip(dev_in.tensors(), template.tensors()):
+                d.copy_(h)
+            with torch.cuda.stream(self.s_run):
+                out = hp.capture(dev_in)
+            host_out = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in self.RESULT_KEYS}
+            self.slots.append(dict(hp=hp, dev_in=dev_in, out=out, host_out=host_out,
+                                   in_ready=torch.cuda.Event(), run_done=torch.cuda.Event(),
+                                   out_done=torch.cuda.Event()))
+        torch.cuda.synchronize(self.device)
+        self.i = 0
+
+    def h2d_bytes(self) -> int:
+        return self.slots[0]["dev_in"].nbytes()
+
+    def d2h_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.slots[0]["host_out"].values())
+
+    def submit(self, pb_host: PairBatch):
+        """Enqueue one host batch (pinned tensors). Returns the slot's pinned host result dict,
+        valid after ``slot['out_done'].synchronize()`` / ``drain()``."""
+        sl = self.slots[self.i % self.depth]
+        self.i += 1
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(sl["run_done"])          # the previous user of these inputs has run
+            for d, h in zip(sl["dev_in"].tensors(), pb_host.tensors()):
+                d.copy_(h, non_blocking=True)
+            sl["in_ready"].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(sl["in_ready"])
+            self.s_run.wait_event(sl["out_done"])         # its previous results have left the device
+            sl["hp"].replay()
+            sl["run_done"].record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(sl["run_done"])
+            for k, h in sl["host_out"].items():
+                h.copy_(sl["out"][k], non_blocking=True)
+            sl["out_done"].record(self.s_out)
+        return sl["host_out"]
+
+    def join(self, stream=None):
+        """Make ``stream`` (default: current) wait for everything submitted so far."""
+        stream = torch.cuda.current_stream(self.device) if stream is None else stream
+        for s in (self.s_in, self.s_run, self.s_out):
+            stream.wait_stream(s)
+
+    def fork(self, stream=None):
+        """Order all three internal streams after ``stream`` (default: current)."""
+        stream = torch.cuda.current_stream(self.device) if stream is None else stream
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(stream)
+
+    def drain(self):
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.synchronize()

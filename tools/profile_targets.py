@@ -1,0 +1,31 @@
+"""Launches each hot kernel twice at BASELINE config-2 size; run under ncu (-k regex ...)."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import stitch_b200 as sb
+from stitch_b200 import corr as C
+
+B, S = 16, 512
+g = torch.Generator(device="cuda").manual_seed(0)
+rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+f1, f2 = rnd(B, 256, 64, 64), rnd(B, 256, 64, 64)
+x6 = torch.rand(B, 6, S, S, device="cuda", generator=g) * 255
+img = torch.rand(B, 3, S, S, device="cuda", generator=g) * 255
+flo = torch.nn.functional.interpolate(rnd(B, 2, 64, 64) * 2, size=(S, S), mode="bilinear", align_corners=True)
+occ = (torch.rand(B, 1, S, S, device="cuda", generator=g) < 0.8).float()
+src = sb.torch_DLT.corner_points(S, S, B, "cuda")
+M = sb.torch_DLT.norm_matrix(S / 8, S / 8)
+coords = sb.lookup.coords_grid(B, 64, 64, device="cuda") + rnd(B, 2, 64, 64) * 2
+for rep in range(2):
+    t1, t2 = C.tokens_bf16(f1), C.tokens_bf16(f2)
+    vol, lv = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_levels=3)
+    vol0 = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64))
+    tok = sb.encode_flow_token(vol.view(B * 4096, 1, 64, 64), coords)
+    H, th, thi = sb.torch_DLT.dlt_thetas(src / 8, (src + 5.0) / 8, left=sb.torch_DLT._inv3(M), right=M)
+    oh = sb.torch_homo_transform.transformer(img, th, (S, S), append_ones=3)
+    o = sb.compute_occlusion(flo, flo, "wang", occlusion_are_zeros=True, threshold=True)
+    fw, ov = sb.warp(x6, flo, mul_mask=occ, return_overlap=True)
+    mo = sb.preprocess_occlusion_mask(occ)
+    torch.cuda.synchronize()
+print("ok")

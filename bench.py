@@ -216,22 +216,30 @@ def run_ours(args):
     barrier()
     launches = _lib.launch_count()
     ms_total = e0.elapsed_time(e1)
-    if args.graph:
-        # events cannot be timed inside a captured graph: the dominant kernel's launches are
-        # timed in an eager pass of the same steps right after (same inputs, same stream)
-        launches = launches_per_step_eager * args.steps
-        hp.gemm_events = []
-        eg0, eg1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eg0.record(stream)
-        for _ in range(args.steps):
-            hp.step(pb_dev)
-        eg1.record(stream)
-        barrier()
-        ms_eager_total = eg0.elapsed_time(eg1)
-    else:
-        ms_eager_total = ms_total
-    gemm_ms = [a.elapsed_time(b) for a, b in hp.gemm_events]
+    gemm_ms = [a.elapsed_time(b) for a, b in (hp.gemm_events or [])]
     hp.gemm_events = None
+    ms_eager_total = ms_total
+    if args.graph:
+        # Events cannot be timed inside a captured graph, and an eager pass of the whole step is
+        # host-bound (event pairs would include launch gaps). The dominant kernel is therefore
+        # timed right after the timed region as back-to-back launches on the same stream, same
+        # operands, each launch writing its full 1.33 GiB of outputs (>> L2).
+        launches = launches_per_step_eager * args.steps
+        from stitch_b200 import corr as corr_mod
+        s8 = SIZE // 8
+        tk1, tk2 = corr_mod.tokens_bf16(pb_dev.fmap1), corr_mod.tokens_bf16(pb_dev.fmap2)
+        for _ in range(3):
+            corr_mod.corr_from_tokens(tk1, tk2, 256, (s8, s8), (s8, s8), pyramid_levels=3)
+        n_rep = 20
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_rep + 1)]
+        evs[0].record(stream)
+        for i in range(n_rep):
+            corr_mod.corr_from_tokens(tk1 if i % 2 == 0 else tk2, tk2 if i % 2 == 0 else tk1, 256, (s8, s8), (s8, s8),
+                                      pyramid_levels=3)
+            evs[i + 1].record(stream)
+        barrier()
+        gemm_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(n_rep)]
+        ms_eager_total = None
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if distributed:
@@ -336,8 +344,10 @@ def run_ours(args):
                          "tensor_tflops": gemm_flops / (gemm_avg_ms / 1000.0) / 1e12,
                          "tensor_frac_of_sustained": (gemm_flops / (gemm_avg_ms / 1000.0) / 1e12) /
                          float(peaks.get("bf16_tflops_sustained", 1400.0)),
-                         "kernel_share_of_step": sum(gemm_ms) / ms_eager_total if gemm_ms else None,
-                         "timed": "CUDA events around every launch, eager pass" + (" after the graph-replay region" if args.graph else " = the timed region")},
+                         "kernel_share_of_step": (2 * gemm_avg_ms / (ms_max / args.steps)) if gemm_ms else None,
+                         "timed": ("CUDA events around 20 back-to-back launches on the launching stream right after the "
+                                   "graph-replay region (events cannot be timed inside a captured graph)") if args.graph
+                         else "CUDA events around every launch inside the timed region (eager)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "wall_ms_per_step": wall_ms / args.steps,

@@ -40,10 +40,13 @@ struct GridTap {
 
   // plane: pointer to the [H, W] channel plane.
   __device__ __forceinline__ float sample(const float* __restrict__ plane, int W) const {
-    float v_nw = m_nw ? __ldg(plane + off_nw) : 0.0f;
-    float v_ne = m_ne ? __ldg(plane + off_nw + 1) : 0.0f;
-    float v_sw = m_sw ? __ldg(plane + off_nw + W) : 0.0f;
-    float v_se = m_se ? __ldg(plane + off_nw + W + 1) : 0.0f;
+    const float* pn = plane + off_nw;     // one 64-bit address per row pair, +1 as an immediate
+    const float* ps = pn + W;
+    float v_nw = 0.0f, v_ne = 0.0f, v_sw = 0.0f, v_se = 0.0f;
+    if (m_nw) v_nw = __ldg(pn);
+    if (m_ne) v_ne = __ldg(pn + 1);
+    if (m_sw) v_sw = __ldg(ps);
+    if (m_se) v_se = __ldg(ps + 1);
     return combine(v_nw, v_ne, v_sw, v_se);
   }
   __device__ __forceinline__ float combine(float v_nw, float v_ne, float v_sw, float v_se) const {

@@ -71,3 +71,34 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "stitch_oracle" not in src and "liboracle" not in src, f
+
+
+def test_patch_reference_assigns_call_sites():
+    """Where the reference is mounted (the build container), patch_reference() must replace
+    exactly the call-site attributes of SURVEY §8(b). The GPU box has no reference: skipped."""
+    import sys
+    ref = os.environ.get("STITCH_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "core")):
+        pytest.skip("reference not mounted")
+    sys.path[:0] = [os.path.join(ROOT, "tests", "golden")]
+    import make_golden
+    saved = dict(sys.modules)
+    saved_path = list(sys.path)
+    try:
+        make_golden.install_shims()
+        import stitch_b200
+        done = stitch_b200.patch_reference()
+        import core.warp_utils as wu
+        import core.udis_utils.torch_homo_transform as th
+        from core.FlowFormer.PerCostFormer3.encoder import MemoryEncoder
+        from core.FlowFormer.PerCostFormer3.decoder import MemoryDecoder
+        assert wu.warp is stitch_b200.warp_utils.warp
+        assert th.transformer is stitch_b200.torch_homo_transform.transformer
+        assert MemoryEncoder.corr is stitch_b200.corr.memory_encoder_corr
+        assert MemoryDecoder.encode_flow_token is stitch_b200.lookup.memory_decoder_encode_flow_token
+        assert len(done) >= 12
+    finally:
+        for k in list(sys.modules):
+            if k not in saved and (k.startswith("core") or k.startswith("timm") or k.startswith("skimage")):
+                del sys.modules[k]
+        sys.path[:] = saved_path

@@ -375,6 +375,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host thread
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = str(os.cpu_count())
         run_reference_arm(args)
     else:
         run_ours(args)

@@ -567,3 +567,36 @@ def test_step_graph_replay_matches_eager(sb):
     for k, v in keep.items():
         assert torch.equal(out[k], v), k
     assert torch.equal(out["cost_tokens"][3], tok)
+
+
+# ===================================================================== config 4: 1024 x 1024 pairs
+def test_corr_1024_pair_and_pyramid(sb):
+    """High-res pair: N = 16384 tokens, 1 GiB volume; W2 = 128 so the pyramid comes from the
+    standalone pooling kernel (a 128-column tile is one target row)."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    f1 = torch.randn(1, 256, 128, 128, device="cuda", generator=g)
+    f2 = torch.randn(1, 256, 128, 128, device="cuda", generator=g)
+    vol, lv = sb.corr.corr(f1, f2, pyramid_levels=3)
+    assert vol.shape == (1, 1, 128, 128, 128, 128)
+    v = vol.view(16384, 16384)
+    a = f1.bfloat16().float().view(256, 16384)
+    b = f2.bfloat16().float().view(256, 16384)
+    scale = None
+    for r0 in (0, 5000, 16384 - 2048):          # row slabs: never materialise a second 1 GiB tensor
+        ref = a[:, r0:r0 + 2048].t() @ b
+        scale = ref.abs().max().item() if scale is None else scale
+        assert (v[r0:r0 + 2048] - ref).abs().max().item() <= 5e-5 * scale
+        ref32 = f1.view(256, 16384)[:, r0:r0 + 2048].t() @ f2.view(256, 16384)
+        assert (v[r0:r0 + 2048] - ref32).abs().max().item() <= 1e-2 * ref32.abs().max().item()
+    cm = vol.view(16384, 1, 128, 128)
+    want = cm
+    for l in range(3):
+        want = torch.nn.functional.avg_pool2d(want, 2, stride=2)
+        assert lv[l].shape == want.shape
+        assert (lv[l] - want).abs().max().item() <= 1e-5 * scale
+    # lookup on the 128x128 maps (queries of one image row), bit-exact vs the oracle
+    coords = sb.lookup.coords_grid(1, 128, 128, device="cuda") + torch.randn(1, 2, 128, 128, device="cuda", generator=g) * 3
+    out = sb.encode_flow_token(cm, coords)
+    sel = slice(128 * 37, 128 * 38)
+    ref = so.encode_flow_token(host(cm[sel]), host(coords[:, :, 37:38, :]))
+    assert_bits_equal(host(out[:, :, 37:38, :].contiguous()), np.ascontiguousarray(ref), "1024^2 lookup")

@@ -51,6 +51,17 @@ int sb_device_check(void);
  * (bench.py's "gpu_launches"). */
 long long sb_launch_count(void);
 void sb_reset_launch_count(void);
+/* Tuning knobs for kernel experiments (tools/, bench sweeps). value 0 restores
+ * the built-in default. Never changes results, only launch geometry (except the
+ * knobs marked EXPERIMENT ONLY, which no product path sets). */
+enum {
+  SB_TUNE_LOOKUP_DEPTH = 0,        /* window groups in flight per warp: 1 or 2 (default) */
+  SB_TUNE_LOOKUP_CTAS_PER_SM = 1,  /* resident CTAs per SM the persistent lookup grid is sized for */
+  SB_TUNE_LOOKUP_SUPERBLOCK = 2,   /* queries per superblock: 8, 16 or 32 (default: by problem size) */
+  SB_TUNE_LOOKUP_FETCH_ONLY = 3,   /* EXPERIMENT ONLY (changes results): windows are fetched, taps are not sampled */
+  SB_TUNE_COUNT = 16
+};
+int sb_tune(int key, int value);
 /* Post-mortem word of the correlation kernel: 0, or 0xDEAD00tt when a bounded
  * mbarrier wait (tag tt) timed out and the kernel trapped instead of hanging. */
 unsigned int sb_debug_word(void);

@@ -28,6 +28,7 @@ SIGNATURES = {
     "sb_launch_count": (c_longlong, []),
     "sb_reset_launch_count": (None, []),
     "sb_debug_word": (c_uint, []),
+    "sb_tune": (c_int, [c_int, c_int]),
     "sb_corr_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "sb_corr": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_feat_to_tokens_bf16": (c_int, [_P, _P, c_int, c_int, c_int, _P]),

@@ -17,6 +17,32 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<int> g_tune[SB_TUNE_COUNT];   // 0 = "use the built-in default"
+int tune_get(int key, int dflt) {
+  if (key < 0 || key >= SB_TUNE_COUNT) return dflt;
+  const int v = g_tune[key].load(std::memory_order_relaxed);
+  return v ? v : dflt;
+}
+
+// Word written (system scope) just before a protocol-timeout trap. It lives in
+// mapped pinned host memory so the host can still read it after the context died.
+static unsigned int* g_dbg_host = nullptr;
+static unsigned int* g_dbg = nullptr;
+unsigned int* debug_word_device() {
+  if (!g_dbg) {
+    cudaError_t e = cudaHostAlloc(&g_dbg_host, 64, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+      *g_dbg_host = 0;
+      e = cudaHostGetDevicePointer(&g_dbg, g_dbg_host, 0);
+    }
+    if (e != cudaSuccess) {
+      set_error("debug word allocation failed: %s", cudaGetErrorString(e));
+      g_dbg = nullptr;
+    }
+  }
+  return g_dbg;
+}
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int check_device() {
@@ -56,6 +82,15 @@ int sb_version(void) { return SB_VERSION; }
 const char* sb_last_error(void) { return sb::g_err; }
 int sb_device_check(void) { return sb::check_device(); }
 long long sb_launch_count(void) { return sb::g_launches.load(std::memory_order_relaxed); }
+unsigned int sb_debug_word(void) { return sb::g_dbg_host ? *sb::g_dbg_host : 0u; }
+int sb_tune(int key, int value) {
+  if (key < 0 || key >= SB_TUNE_COUNT) {
+    sb::set_error("sb_tune: unknown key %d", key);
+    return SB_EINVAL;
+  }
+  sb::g_tune[key].store(value, std::memory_order_relaxed);
+  return SB_OK;
+}
 void sb_reset_launch_count(void) { sb::g_launches.store(0, std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -18,6 +18,8 @@ namespace sb {
 void set_error(const char* fmt, ...);
 int check_device();          // SB_OK if the current device is sm_100
 void count_launch(int n = 1);
+unsigned int* debug_word_device();   // mapped host word for bounded-wait post-mortems (nullptr on failure)
+int tune_get(int key, int dflt);   // sb_tune() override, else dflt
 
 #define SB_REQUIRE(cond, code, ...)                 \
   do {                                              \

@@ -14,6 +14,8 @@
 // HBM-bound gather. Algorithmic bytes per query (r = 4): (2r+2)^2*4 = 400 read
 // + 8 coords + (2r+1)^2*4 = 324 written = 732 B.
 #include "bilinear.cuh"
+#include "ptx_sm100.cuh"
+#include "tmap.cuh"
 
 namespace sb {
 
@@ -112,126 +114,334 @@ corr_lookup_kernel(const float* __restrict__ cost_maps, const float* __restrict_
 // ---------------------------------------------------------------------------
 // Fast path: r = 4 (the only radius the reference uses), W2 % 4 == 0.
 // The generic kernel above is instruction-bound (~1000 issued instructions per
-// query: per-tap divisions, runtime index divisions, masks).  Here
+// query) and exposes two dependent DRAM round trips (coords -> window) per CTA.
+// Here the window fetch is handed to the TMA and the warps only do arithmetic:
+//   * cost_maps is described to the TMA as a 3-D tensor {W2, H2, B*H1*W1}; the
+//     window of a query is ONE cp.async.bulk.tensor of a 12|16 x 10|12 box whose
+//     corner is the query's exact minimum tap (xmin & ~3, ymin) — negative or
+//     past-the-edge coordinates included: the hardware zero-fills
+//     what lies outside the map, which IS grid_sample's zeros padding (an
+//     out-of-range tap multiplies its weight by 0.0 in the same fma chain), so
+//     neither the fetch nor the taps need masks or address arithmetic;
+//   * persistent warps walk groups of 4 consecutive queries through a software
+//     pipeline: the boxes of groups i+1..i+D are in flight into a ring of D+1
+//     shared-memory buffers (one mbarrier each) while group i is sampled;
+//   * a "superblock" is 8/16/32 consecutive queries of one batch element; a warp
+//     loads its x- and y-centres with ONE coalesced load each (lane l holds
+//     query l) and keeps the next superblock's in registers too, so the only
+//     dependent DRAM round trip left in the loop is the window;
 //   * the 9 x- and 9 y-coordinates of a query are round-tripped ONCE by lanes
-//     0..17 (the 81 taps are their outer product) and shared with shuffles;
-//   * the window is zero-filled in shared memory, which IS grid_sample's zeros
-//     padding (an out-of-range tap multiplies its weight by 0.0 in the same fma
-//     chain), so the taps need no masks;
-//   * lane l < 27 owns window row pair j = l % 9 and the three x-positions
-//     i = 3*(l/9) + {0,1,2}: 8 shared-memory loads feed 3 taps;
-//   * all index math is 32-bit and compile-time where possible.
-// A query whose taps do not fit the staged window (non-finite coordinates) is
-// handled by the generic per-tap gather.
-constexpr int kFastR = 4, kFastSide = 9;
-constexpr int kFastRows = 12, kFastPitch = 20;   // 12 x 16 floats, rows padded to 20 words
-constexpr int kFastQ = 4;                        // queries per warp, all loads issued up front
+//     0..17 (the 81 taps are their outer product) and parked next to the window
+//     in shared memory; the round trip is monotone, so lanes 0 and 9 hold the
+//     exact minimum floors. The IEEE division by (size-1) is done with a
+//     correctly-rounded reciprocal and one exact-residual fma step (same
+//     result as div.rn, no range check / slow-path call);
+//   * lane l < 27 owns x-position i = l % 9 and the three y-positions
+//     j = 3*(l/9) + {0,1,2} (lanes of a row group read 9 different columns:
+//     at most 2-way bank conflicts on the dense TMA rows);
+//   * the 4 x 81 results of a group are staged in shared memory and leave as
+//     81 coalesced 16-byte stores.
+// A query whose taps do not fit the 16 x 12 box (cannot happen for finite
+// coordinates) is handled by the generic per-tap gather.
+constexpr int kFastR = 4, kFastSide = 9, kFastTaps = 81;
+constexpr int kFastQ = 4;                        // queries per group
+constexpr int kBoxWMax = 16, kBoxHMax = 12;      // largest TMA box: 16 floats x 12 rows
+constexpr int kWinBytes = kBoxWMax * kBoxHMax * 4;   // 768 (a multiple of 128: TMA destination alignment)
+constexpr int kAxisBytes = 160;                  // int2 {floor, frac bits} x 18, then {fits, row pitch}
+constexpr int kAxisOff = kFastQ * kWinBytes;     // the 4 axis tables follow the 4 windows
+constexpr int kGroupBytes = kFastQ * (kWinBytes + kAxisBytes);   // 3712 = 29 * 128
+constexpr int kStageBytes = 1408;                // 4 * 81 * 4 = 1296 -> next multiple of 128
+// The TMA wants 16-byte aligned box corners, so a window starts at ax = xmin & ~3 and is
+// 12 floats wide when the 10-11 columns the taps touch end before ax + 12 (3 times out of 4),
+// else 16; 10 rows when the y-floors are the regular ymin..ymin+8, else 12. One tensor map each.
+struct LookupMaps {
+  CUtensorMap m[4];                              // [wide + 2 * tall]
+};
+__host__ __device__ constexpr int fast_warp_bytes(int depth) {
+  return (depth + 1) * kGroupBytes + kStageBytes + 128;   // ring + output stage + mbarriers
+}
+__host__ __device__ constexpr int fast_smem_bytes(int depth) {
+  return kLookupWarps * fast_warp_bytes(depth) + 128;     // + alignment slack
+}
+static_assert(kGroupBytes % 128 == 0 && kWinBytes % 128 == 0 && 19 * 8 <= kAxisBytes, "slot layout");
 
-// grid = (ceil(HW1 / 32), B): a CTA owns 32 consecutive queries of one batch element,
-// warp w the 4 queries [4w, 4w+4) — no index divisions, and 4 x (1 + 2) independent
-// global loads in flight per warp hide the two dependent DRAM round trips.
-__global__ void __launch_bounds__(kLookupWarps * 32)
-corr_lookup_r4_kernel(const float* __restrict__ cost_maps, const float* __restrict__ coords,
-                      float* __restrict__ out, int HW1, int H2, int W2, float coord_scale,
-                      int out_stride, int out_offset) {
-  __shared__ __align__(16) float s_win[kLookupWarps][kFastQ][kFastRows * kFastPitch];
+struct FastLane {   // per-lane constants of the r = 4 kernel
+  float den, rcp, half, coff, scale;
+};
+
+// Per-axis position of this lane's coordinate (lanes 0..8: x + lane-4, lanes 9..17: y + lane-13):
+// grid_roundtrip() with the division restated as a correctly rounded reciprocal and one
+// exact-residual fma correction (== div.rn for operands in the normal range, proven exhaustively
+// on the CPU for every mantissa and every integer denominator up to 2047). Returns true
+// when the operand is outside that range and fast_axis_exact() must be used instead.
+__device__ __forceinline__ bool fast_axis(const FastLane& L, float c_raw, int& fi, float& frac) {
+  const float a = fmul(2.0f, fadd(fmul(c_raw, L.scale), L.coff));
+  float q = fmul(a, L.rcp);
+  q = __fmaf_rn(__fmaf_rn(-q, L.den, a), L.rcp, q);   // Markstein: exact for integer den <= 2047 (tests/test_div_restatement.py)
+  const float t = fmul(fadd(fsub(q, 1.0f), 1.0f), L.half);
+  const float fl = floorf(t);
+  frac = fsub(t, fl);
+  fi = sat_floor_to_int(fl, -100000, 100000);
+  const float aa = fabsf(a);
+  return !((aa > 1e-30f && aa < 1e30f) || aa == 0.0f);   // denormal range / huge / non-finite
+}
+__device__ __noinline__ void fast_axis_exact(const FastLane& L, float c_raw, int& fi, float& frac) {
+  const float t = grid_roundtrip(fadd(fmul(c_raw, L.scale), L.coff), L.den, L.half);
+  const float fl = floorf(t);
+  frac = fsub(t, fl);
+  fi = sat_floor_to_int(fl, -100000, 100000);
+}
+
+struct FastSb {     // a superblock: this lane's query centre + where the superblock starts
+  float x, y;
+  int b, pos;
+};
+
+template <int kFastDepth>
+__global__ void __launch_bounds__(kLookupWarps * 32, kFastDepth == 1 ? 3 : 2)
+corr_lookup_r4_kernel(const __grid_constant__ LookupMaps maps, const float* __restrict__ cost_maps,
+                      const float* __restrict__ coords, float* __restrict__ out, int B, int HW1,
+                      int H2, int W2, float coord_scale, int out_stride, int out_offset, int vec_out,
+                      int sbq, unsigned int* dbg) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  constexpr int kBufs = kFastDepth + 1;
+  constexpr unsigned kFull = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int pos0 = blockIdx.x * (kLookupWarps * kFastQ) + warp * kFastQ;
-  if (pos0 >= HW1) return;
-  const float denx = (float)(W2 - 1), deny = (float)(H2 - 1);
-  const float halfx = fmul((float)(W2 - 1), 0.5f), halfy = fmul((float)(H2 - 1), 0.5f);  // == /2 exactly
-  const int map_sz = H2 * W2;
-  // lane roles
-  const bool is_x = lane < kFastSide;
-  const int cidx = is_x ? lane : (lane < 2 * kFastSide ? lane - kFastSide : 0);
-  const float cden = is_x ? denx : deny, chalf = is_x ? halfx : halfy;
-  const float coff = (float)(cidx - kFastR);
-  const int tj = lane % kFastSide, tig = (lane / kFastSide) % 3;   // tap row / x-group (lanes >= 27 idle)
-  const int wrow0 = lane >> 2, wch = lane & 3;                     // window chunk owned in pass 0
-  const float* cbase = coords + ((size_t)b * 2 + (is_x ? 0 : 1)) * HW1 + pos0;
-  const size_t q0 = (size_t)b * HW1 + pos0;
+  const uint32_t raw_u32 = ptx::smem_u32(s_raw);
+  const uint32_t w_u32 = ((raw_u32 + 127u) & ~127u) + warp * fast_warp_bytes(kFastDepth);
+  unsigned char* w_gen = s_raw + (w_u32 - raw_u32);
+  float* s_stage = reinterpret_cast<float*>(w_gen + kBufs * kGroupBytes);
+  const uint32_t bar0 = w_u32 + kBufs * kGroupBytes + kStageBytes;
 
-  // ---- phase A: the 4 centre coordinates (independent loads)
-  float c_raw[kFastQ];
+  if (lane == 0) {
 #pragma unroll
-  for (int k = 0; k < kFastQ; ++k) c_raw[k] = (pos0 + k < HW1) ? __ldg(cbase + k) : 0.0f;
-
-  // ---- phase B: per-axis round trips, window origins, window loads (8 x LDG.128 in flight)
-  int fi[kFastQ], wy0[kFastQ], ax[kFastQ];
-  float wfrac[kFastQ];
-  float4 v0[kFastQ], v1[kFastQ];
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tensormap(&maps.m[i]);
 #pragma unroll
-  for (int k = 0; k < kFastQ; ++k) {
-    const float t = grid_roundtrip(fadd(fmul(c_raw[k], coord_scale), coff), cden, chalf);
-    const float fl = floorf(t);
-    wfrac[k] = fsub(t, fl);
-    fi[k] = sat_floor_to_int(fl, -100000, 100000);
-    const int x0i = __shfl_sync(0xffffffffu, fi[k], 0), y0i = __shfl_sync(0xffffffffu, fi[k], kFastSide);
-    wy0[k] = y0i - 1;
-    ax[k] = (x0i - 1) & ~3;
-    const float* map = cost_maps + (q0 + k) * map_sz;
-    const int gx = ax[k] + wch * 4;
-    const bool xin = (gx >= 0) & (gx + 3 < W2) & (pos0 + k < HW1);
-    const int gy = wy0[k] + wrow0;
-    v0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    v1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (xin & (gy >= 0) & (gy < H2)) v0[k] = ldg_stream4(map + gy * W2 + gx);
-    if (xin & (lane < 16) & (gy + 8 >= 0) & (gy + 8 < H2)) v1[k] = ldg_stream4(map + (gy + 8) * W2 + gx);
-  }
-#pragma unroll
-  for (int k = 0; k < kFastQ; ++k) {
-    float* win = s_win[warp][k];
-    *reinterpret_cast<float4*>(win + wrow0 * kFastPitch + wch * 4) = v0[k];
-    if (lane < 16) *reinterpret_cast<float4*>(win + (wrow0 + 8) * kFastPitch + wch * 4) = v1[k];
+    for (int i = 0; i < kBufs; ++i) ptx::mbar_init(bar0 + 8 * i, 1);
+    ptx::fence_mbar_init();
   }
   __syncwarp();
 
-  // ---- phase C: taps
-#pragma unroll
-  for (int k = 0; k < kFastQ; ++k) {
-    if (pos0 + k >= HW1) break;                                    // warp-uniform
-    const float* win = s_win[warp][k];
-    const int yn = __shfl_sync(0xffffffffu, fi[k], kFastSide + tj);
-    const float n = __shfl_sync(0xffffffffu, wfrac[k], kFastSide + tj);
-    int xw[3];
-    float wv[3];
-#pragma unroll
-    for (int m = 0; m < 3; ++m) {
-      xw[m] = __shfl_sync(0xffffffffu, fi[k], 3 * tig + m);
-      wv[m] = __shfl_sync(0xffffffffu, wfrac[k], 3 * tig + m);
+  FastLane L;
+  const bool is_x = lane < kFastSide;
+  const int cidx = is_x ? lane : (lane < 2 * kFastSide ? lane - kFastSide : 0);
+  L.den = is_x ? (float)(W2 - 1) : (float)(H2 - 1);
+  L.rcp = __frcp_rn(L.den);
+  L.half = fmul(L.den, 0.5f);                                     // == (size-1)/2 exactly
+  L.coff = (float)(cidx - kFastR);
+  L.scale = coord_scale;
+  const int map_sz = H2 * W2;
+  const int ti = lane % kFastSide, tjg = (lane / kFastSide) % 3;  // tap x-position / y-group (lanes >= 27 idle)
+
+  const int sbq_flags = sbq;
+  sbq &= 0xff;
+  const int gps = sbq / kFastQ;                                   // groups per superblock (>= kFastDepth)
+  const int sb_per_b = (HW1 + sbq - 1) / sbq;
+  const int n_sb = B * sb_per_b;
+  const int n_warps = gridDim.x * kLookupWarps;
+  const int sb0 = warp * gridDim.x + blockIdx.x;                  // CTA-interleaved: small problems spread over SMs
+  if (sb0 >= n_sb) return;
+  const int n_my_sb = (n_sb - sb0 + n_warps - 1) / n_warps;
+  const int n_my = n_my_sb * gps;                                 // groups (some may be empty at a ragged HW1 tail)
+
+  auto load_sb = [&](int t) {
+    FastSb S;
+    S.x = 0.0f; S.y = 0.0f; S.b = 0; S.pos = HW1;
+    if (t < n_my_sb) {
+      const int sbi = sb0 + t * n_warps;
+      S.b = sbi / sb_per_b;
+      S.pos = (sbi - S.b * sb_per_b) * sbq;
+      if (lane < sbq && S.pos + lane < HW1) {
+        const float* cb = coords + (size_t)S.b * 2 * HW1 + S.pos + lane;
+        S.x = __ldg(cb);
+        S.y = __ldg(cb + HW1);
+      }
     }
-    const int ly = yn - wy0[k];
-    bool fits = (ly >= 0) & (ly + 1 < kFastRows);
+    return S;
+  };
+
+  FastSb cur = load_sb(0), nxt = load_sb(1);
+  int t_cur = 0;                               // superblock of the group being sampled
+  int f_t = 0, f_in = 0, f_buf = 0;            // front cursor: superblock, group in it, ring slot
+
+  // ---- front: axis tables + TMA boxes of one group (the 4 queries in lock step for ILP)
+  auto front = [&]() {
+    if (f_t < n_my_sb) {
+      const bool use_cur = (f_t == t_cur);
+      const float sx = use_cur ? cur.x : nxt.x, sy = use_cur ? cur.y : nxt.y;
+      const int b = use_cur ? cur.b : nxt.b;
+      const int pos0 = (use_cur ? cur.pos : nxt.pos) + f_in * kFastQ;
+      unsigned char* gbuf = w_gen + f_buf * kGroupBytes;
+      const uint32_t gbuf_u32 = w_u32 + f_buf * kGroupBytes;
+      const uint32_t bar = bar0 + 8 * f_buf;
+      const int q0 = b * HW1 + pos0;
+      const int nvalid = HW1 - pos0;                              // queries k < nvalid exist
+      float c[kFastQ];
 #pragma unroll
-    for (int m = 0; m < 3; ++m) fits &= (xw[m] - ax[k] >= 0) & (xw[m] - ax[k] + 1 < 16);
-    const bool all_fit = __all_sync(0xffffffffu, fits | (lane >= 27));
-    float* orow = out + (q0 + k) * out_stride + out_offset;
-    if (all_fit) {
+      for (int k = 0; k < kFastQ; ++k) {
+        const int src = f_in * kFastQ + k;
+        const float vx = __shfl_sync(kFull, sx, src), vy = __shfl_sync(kFull, sy, src);
+        c[k] = is_x ? vx : vy;
+      }
+      int fi[kFastQ];
+      float fr[kFastQ];
+      bool odd = false;
+#pragma unroll
+      for (int k = 0; k < kFastQ; ++k) odd |= fast_axis(L, c[k], fi[k], fr[k]);
+      if (__any_sync(kFull, odd)) {
+#pragma unroll
+        for (int k = 0; k < kFastQ; ++k) fast_axis_exact(L, c[k], fi[k], fr[k]);
+      }
+      int ax[kFastQ], ymin[kFastQ];
+      unsigned big[kFastQ], over[kFastQ];
+      int hflag[kFastQ];                                          // bit 0 fits, bit 1 regular, bits 2-3 xmin & 3
+#pragma unroll
+      for (int k = 0; k < kFastQ; ++k) {
+        const int xmin = __shfl_sync(kFull, fi[k], 0);
+        ymin[k] = __shfl_sync(kFull, fi[k], kFastSide);
+        ax[k] = xmin & ~3;
+        // taps reach floor+1: span = last column / row touched, relative to the box corner
+        const int span = (lane < 2 * kFastSide) ? fi[k] + 1 - (is_x ? ax[k] : ymin[k]) : 0;
+        big[k] = __ballot_sync(kFull, span >= (is_x ? 12 : 10));
+        over[k] = __ballot_sync(kFull, span >= (is_x ? kBoxWMax : kBoxHMax));
+        // regular = every floor is min + tap index (no ulp wobble across an integer): rows / columns are consecutive
+        const bool irregular = (lane < 2 * kFastSide) & (fi[k] - (is_x ? xmin : ymin[k]) != cidx);
+        hflag[k] = (over[k] == 0u ? 1 : 0) | (__any_sync(kFull, irregular) ? 0 : 2) | ((xmin & 3) << 2);
+      }
+#pragma unroll
+      for (int k = 0; k < kFastQ; ++k) {
+        int2* axis = reinterpret_cast<int2*>(gbuf + kAxisOff + k * kAxisBytes);
+        const int bw = (big[k] & 0x1ffu) ? 16 : 12;
+        if (lane < 2 * kFastSide) axis[lane] = make_int2(fi[k], __float_as_int(fr[k]));
+        else if (lane == 2 * kFastSide) axis[lane] = make_int2(hflag[k], bw);
+      }
+      if (lane == 0) {
+        uint32_t tx = 0;
+#pragma unroll
+        for (int k = 0; k < kFastQ; ++k) {
+          if (k < nvalid && over[k] == 0u) {
+            const int wide = (big[k] & 0x1ffu) ? 1 : 0, tall = (big[k] >> kFastSide) ? 1 : 0;
+            ptx::tma_load_3d(gbuf_u32 + k * kWinBytes, &maps.m[wide + 2 * tall], bar, ax[k], ymin[k], q0 + k);
+            tx += (wide ? 16 : 12) * (tall ? 12 : 10) * 4;
+          }
+        }
+        ptx::mbar_arrive_expect_tx(bar, tx);
+      }
+      __syncwarp();
+    }
+    if (++f_in == gps) { f_in = 0; ++f_t; }
+    if (++f_buf == kBufs) f_buf = 0;
+  };
+
+#pragma unroll
+  for (int d = 0; d < kFastDepth; ++d) front();
+
+  int b_in = 0, b_buf = 0;
+  uint32_t b_par = 0;
+  for (int i = 0; i < n_my; ++i) {
+    front();                                                      // group i + D
+    ptx::mbar_wait(bar0 + 8 * b_buf, b_par, 0x40 + b_buf, dbg);   // boxes of group i have landed
+    const int pos0 = cur.pos + b_in * kFastQ;
+    const size_t q0 = (size_t)cur.b * HW1 + pos0;
+    const int nvalid = HW1 - pos0;
+    const unsigned char* gbuf = w_gen + b_buf * kGroupBytes;
+    int2 hdr[kFastQ];                                             // {fits, row pitch}
+#pragma unroll
+    for (int k = 0; k < kFastQ; ++k)
+      hdr[k] = reinterpret_cast<const int2*>(gbuf + kAxisOff + k * kAxisBytes)[2 * kFastSide];
+    if (sbq_flags & 0x100) {
+      // experiment knob (tools/lookup_exp.py): fetch only, no sampling
+    } else if (nvalid >= kFastQ && ((hdr[0].x & hdr[1].x & hdr[2].x & hdr[3].x) & 3) == 3) {
+      // ---- hot path: all 4 queries fit and are regular -> window rows 3*tjg .. 3*tjg+3, columns
+      // (xmin & 3) + ti, +1; 4 queries in lock step, 48 independent shared-memory loads per lane
       if (lane < 27) {
-        const float s = fsub(1.0f, n);
+        float v[kFastQ][4][2], w[kFastQ], n[kFastQ][3];
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-          const float w = wv[m], e = fsub(1.0f, w);
-          const float* wp = win + ly * kFastPitch + (xw[m] - ax[k]);
-          const float v_nw = wp[0], v_ne = wp[1], v_sw = wp[kFastPitch], v_se = wp[kFastPitch + 1];
-          const float nw = fmul(s, e), ne = fmul(s, w), sw = fmul(n, e), se = fmul(n, w);
-          orow[(3 * tig + m) * kFastSide + tj] =
-              __fmaf_rn(v_se, se, __fmaf_rn(v_sw, sw, __fmaf_rn(v_ne, ne, fmul(v_nw, nw))));
+        for (int k = 0; k < kFastQ; ++k) {
+          const int pitch = hdr[k].y;
+          const float* base = reinterpret_cast<const float*>(gbuf + k * kWinBytes) + (hdr[k].x >> 2) + ti +
+                              3 * tjg * pitch;
+          const int2* axis = reinterpret_cast<const int2*>(gbuf + kAxisOff + k * kAxisBytes);
+          w[k] = __int_as_float(axis[ti].y);
+#pragma unroll
+          for (int m = 0; m < 3; ++m) n[k][m] = __int_as_float(axis[kFastSide + 3 * tjg + m].y);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            v[k][r][0] = base[r * pitch];
+            v[k][r][1] = base[r * pitch + 1];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kFastQ; ++k) {
+          const float e = fsub(1.0f, w[k]);
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            const float s = fsub(1.0f, n[k][m]);
+            const float nw = fmul(s, e), ne = fmul(s, w[k]), sw = fmul(n[k][m], e), se = fmul(n[k][m], w[k]);
+            s_stage[k * kFastTaps + ti * kFastSide + 3 * tjg + m] = __fmaf_rn(
+                v[k][m + 1][1], se,
+                __fmaf_rn(v[k][m + 1][0], sw, __fmaf_rn(v[k][m][1], ne, fmul(v[k][m][0], nw))));
+          }
         }
       }
     } else {
-      // cold path (non-finite coordinates): per-tap masked gather straight from global memory
-      const float* cb = coords + (size_t)b * 2 * HW1 + pos0 + k;
-      const float cx = fmul(__ldg(cb), coord_scale), cy = fmul(__ldg(cb + HW1), coord_scale);
-      const float* map = cost_maps + (q0 + k) * map_sz;
-      for (int t = lane; t < kFastSide * kFastSide; t += 32) {
-        const int i = t / kFastSide, j = t - i * kFastSide;
-        GridTap tap;
-        tap.setup(grid_roundtrip(fadd(cx, (float)(i - kFastR)), denx, halfx),
-                  grid_roundtrip(fadd(cy, (float)(j - kFastR)), deny, halfy), H2, W2);
-        orow[t] = tap.sample(map, W2);
+      // ---- ragged tail of a batch element, or a query whose taps do not fit the box
+      for (int k = 0; k < kFastQ && k < nvalid; ++k) {
+        const float* win = reinterpret_cast<const float*>(gbuf + k * kWinBytes);
+        const int2* axis = reinterpret_cast<const int2*>(gbuf + kAxisOff + k * kAxisBytes);
+        const int2 h = axis[2 * kFastSide];
+        float* srow = s_stage + k * kFastTaps;
+        if (h.x & 1) {
+          if (lane < 27) {
+            const int ax = axis[0].x & ~3, ymin = axis[kFastSide].x;
+            const int2 axx = axis[ti];
+            const float wq = __int_as_float(axx.y), e = fsub(1.0f, wq);
+            for (int m = 0; m < 3; ++m) {
+              const int2 ay = axis[kFastSide + 3 * tjg + m];
+              const float nq = __int_as_float(ay.y), s = fsub(1.0f, nq);
+              const float* p = win + (ay.x - ymin) * h.y + (axx.x - ax);
+              const float v_nw = p[0], v_ne = p[1], v_sw = p[h.y], v_se = p[h.y + 1];
+              const float nw = fmul(s, e), ne = fmul(s, wq), sw = fmul(nq, e), se = fmul(nq, wq);
+              srow[ti * kFastSide + 3 * tjg + m] =
+                  __fmaf_rn(v_se, se, __fmaf_rn(v_sw, sw, __fmaf_rn(v_ne, ne, fmul(v_nw, nw))));
+            }
+          }
+        } else {
+          // cold path: per-tap masked gather straight from global memory
+          const float* cb = coords + (size_t)cur.b * 2 * HW1 + pos0 + k;
+          const float cx = fmul(__ldg(cb), coord_scale), cy = fmul(__ldg(cb + HW1), coord_scale);
+          const float* map = cost_maps + (q0 + k) * map_sz;
+          const float denx = (float)(W2 - 1), deny = (float)(H2 - 1);
+          const float halfx = fmul(denx, 0.5f), halfy = fmul(deny, 0.5f);
+          for (int t = lane; t < kFastTaps; t += 32) {
+            const int tx = t / kFastSide, ty = t - tx * kFastSide;
+            GridTap tap;
+            tap.setup(grid_roundtrip(fadd(cx, (float)(tx - kFastR)), denx, halfx),
+                      grid_roundtrip(fadd(cy, (float)(ty - kFastR)), deny, halfy), H2, W2);
+            srow[t] = tap.sample(map, W2);
+          }
+        }
       }
+    }
+    __syncwarp();
+    // ---- results leave coalesced
+    if (vec_out && nvalid >= kFastQ) {
+      float4* o4 = reinterpret_cast<float4*>(out + q0 * kFastTaps);
+      const float4* s4 = reinterpret_cast<const float4*>(s_stage);
+#pragma unroll
+      for (int t = lane; t < kFastTaps; t += 32) stg_stream4(reinterpret_cast<float*>(o4 + t), s4[t]);
+    } else {
+      for (int k = 0; k < kFastQ && k < nvalid; ++k) {
+        float* orow = out + (q0 + k) * out_stride + out_offset;
+        for (int t = lane; t < kFastTaps; t += 32) orow[t] = s_stage[k * kFastTaps + t];
+      }
+    }
+    if (++b_buf == kBufs) { b_buf = 0; b_par ^= 1u; }
+    if (++b_in == gps) {                                          // next superblock becomes current
+      b_in = 0;
+      ++t_cur;
+      cur = nxt;
+      nxt = load_sb(t_cur + 1);
     }
   }
 }
@@ -277,11 +487,44 @@ extern "C" int sb_corr_lookup(const float* cost_maps, const float* coords, float
   long long blocks = (nq + kLookupWarps - 1) / kLookupWarps;
   const long long max_blocks = (long long)kNumSMs * 8 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
-  if (r == kFastR && (W2 & 3) == 0 && B <= 65535) {
-    const int hw1 = H1 * W1, per_cta = kLookupWarps * kFastQ;
-    dim3 grid((hw1 + per_cta - 1) / per_cta, B);
-    corr_lookup_r4_kernel<<<grid, kLookupWarps * 32, 0, as_stream(stream)>>>(
-        cost_maps, coords, out, hw1, H2, W2, coord_scale, out_stride, out_offset);
+  if (r == kFastR && (W2 & 3) == 0 && nq < (1ll << 30) && W2 <= 2048 && H2 <= 2048) {
+    const int hw1 = H1 * W1;
+    const int vec_out = (out_stride == kFastTaps && out_offset == 0 && (hw1 % kFastQ) == 0 && aligned16(out)) ? 1 : 0;
+    const int depth = tune_get(SB_TUNE_LOOKUP_DEPTH, 2);
+    int per_sm = tune_get(SB_TUNE_LOOKUP_CTAS_PER_SM, 0);
+    unsigned int* dbg_word = debug_word_device();
+    if (!dbg_word) return SB_ECUDA;
+    LookupMaps maps;
+    for (int v = 0; v < 4; ++v) {
+      const int rc = make_map_3d_ex(&maps.m[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cost_maps,
+                                    (unsigned long long)W2, (unsigned long long)H2, (unsigned long long)nq,
+                                    (v & 1) ? 16 : 12, (v & 2) ? 12 : 10, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, "cost_maps");
+      if (rc != SB_OK) return rc;
+    }
+#define SB_LAUNCH_R4(D)                                                                              \
+    do {                                                                                             \
+      static bool attr_set = false;                                                                  \
+      if (!attr_set) {                                                                               \
+        SB_CUDA(cudaFuncSetAttribute(corr_lookup_r4_kernel<D>,                                       \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, fast_smem_bytes(D))); \
+        attr_set = true;                                                                             \
+      }                                                                                              \
+      if (per_sm <= 0) per_sm = (D == 1) ? 3 : 2;                                                                   \
+      const long long resident_warps = (long long)kNumSMs * per_sm * kLookupWarps;                    \
+      int sbq = tune_get(SB_TUNE_LOOKUP_SUPERBLOCK, 0);                                              \
+      if (sbq != 8 && sbq != 16 && sbq != 32)                                                        \
+        sbq = (nq >= resident_warps * 24) ? 32 : (nq >= resident_warps * 12 ? 16 : 8);               \
+      if (sbq < D * kFastQ) sbq = 16;                                                                \
+      const long long n_sb = (long long)B * ((hw1 + sbq - 1) / sbq);                                 \
+      long long ctas = n_sb < (long long)kNumSMs * per_sm ? n_sb : (long long)kNumSMs * per_sm;      \
+      corr_lookup_r4_kernel<D><<<(int)ctas, kLookupWarps * 32, fast_smem_bytes(D), as_stream(stream)>>>( \
+          maps, cost_maps, coords, out, B, hw1, H2, W2, coord_scale, out_stride, out_offset, vec_out, \
+          sbq | (tune_get(SB_TUNE_LOOKUP_FETCH_ONLY, 0) ? 0x100 : 0), dbg_word);                                                                            \
+    } while (0)
+    if (depth == 1) SB_LAUNCH_R4(1);
+    else SB_LAUNCH_R4(2);
+#undef SB_LAUNCH_R4
     SB_LAUNCH_CHECK("corr_lookup_r4_kernel");
     return SB_OK;
   }

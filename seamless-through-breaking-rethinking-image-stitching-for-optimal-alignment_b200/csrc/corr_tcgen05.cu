@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include "tmap.cuh"
 
 namespace sb {
 
@@ -375,55 +376,18 @@ avg_pool2x2_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
 }
 
 // --------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* ptr = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
-    set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
-    return nullptr;
-  }
-  fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  return fn;
-}
-
 static int make_map_3d(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base,
                        unsigned long long d0, unsigned long long d1, unsigned long long d2,
                        unsigned b0, unsigned b1, const char* what) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return SB_ECUDA;
-  cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * (unsigned long long)elt_bytes, d0 * d1 * (unsigned long long)elt_bytes};
-  cuuint32_t box[3] = {b0, b1, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu x %llu x %llu)", what,
-              (int)r, d0, d1, d2);
-    return SB_ECUDA;
-  }
-  return SB_OK;
+  return make_map_3d_ex(m, dt, elt_bytes, base, d0, d1, d2, b0, b1, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, what);
 }
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // Word written (system scope) just before a protocol-timeout trap. It lives in
 // mapped pinned host memory so the host can still read it after the context died.
-static unsigned int* g_dbg_host = nullptr;
-static unsigned int* g_dbg = nullptr;
-
 }  // namespace sb
-
-extern "C" unsigned int sb_debug_word(void) { return sb::g_dbg_host ? *sb::g_dbg_host : 0u; }
 
 extern "C" size_t sb_corr_workspace_bytes(int B, int C, int N1, int N2) {
   if (B < 0 || C < 0 || N1 < 0 || N2 < 0) return 0;
@@ -512,10 +476,9 @@ extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, fl
     if (rc) return rc;
   }
 
+  unsigned int* g_dbg = debug_word_device();
   if (!g_dbg) {
-    SB_CUDA(cudaHostAlloc(&g_dbg_host, 64, cudaHostAllocMapped));
-    *g_dbg_host = 0;
-    SB_CUDA(cudaHostGetDevicePointer(&g_dbg, g_dbg_host, 0));
+    return SB_ECUDA;
   }
 
   CorrParams p;

@@ -1,0 +1,17 @@
+"""Three full-size lookups (B=16, 512^2) for an ncu capture of corr_lookup_r4_kernel."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import stitch_b200 as sb
+from stitch_b200 import corr as C
+B, n = 16, 4096
+g = torch.Generator(device="cuda").manual_seed(0)
+f1 = torch.randn(B, 256, 64, 64, device="cuda", generator=g)
+f2 = torch.randn(B, 256, 64, 64, device="cuda", generator=g)
+maps = C.corr(f1, f2).view(B * n, 1, 64, 64)
+for it in range(3):
+    coords = sb.lookup.coords_grid(B, 64, 64, device="cuda") + torch.randn(B, 2, 64, 64, device="cuda", generator=g) * 2
+    out = sb.encode_flow_token(maps, coords)
+torch.cuda.synchronize()
+print("ok")

@@ -49,6 +49,16 @@ struct GridTap {
     if (m_se) v_se = __ldg(ps + 1);
     return combine(v_nw, v_ne, v_sw, v_se);
   }
+  // pn / ps: the north / south tap rows of this pixel in one channel plane (plane + off_nw, + W);
+  // callers step both by the plane stride from channel to channel (one 64-bit add each).
+  __device__ __forceinline__ float sample_rows(const float* __restrict__ pn, const float* __restrict__ ps) const {
+    float v_nw = 0.0f, v_ne = 0.0f, v_sw = 0.0f, v_se = 0.0f;
+    if (m_nw) v_nw = __ldg(pn);
+    if (m_ne) v_ne = __ldg(pn + 1);
+    if (m_sw) v_sw = __ldg(ps);
+    if (m_se) v_se = __ldg(ps + 1);
+    return combine(v_nw, v_ne, v_sw, v_se);
+  }
   __device__ __forceinline__ float combine(float v_nw, float v_ne, float v_sw, float v_se) const {
     // ATen's CPU build contracts the mul/add chain into FMAs (bit-exact vs F.grid_sample)
     return __fmaf_rn(v_se, se, __fmaf_rn(v_sw, sw, __fmaf_rn(v_ne, ne, fmul(v_nw, nw))));

@@ -15,7 +15,7 @@
 
 namespace sb {
 
-template <int C_T>
+template <int C_T, bool EXACT_RCP>
 __global__ void __launch_bounds__(256)
 flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flo,
                  const float* __restrict__ mul_mask, float* __restrict__ out,
@@ -35,25 +35,38 @@ flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flo,
   const float m = mul_mask ? ldg_stream(mul_mask + (size_t)b * plane + rem) : 1.0f;
   // grid + flow (coords_grid is exact integers as float), then the round trip.
   GridTap tap;
-  tap.setup(grid_roundtrip(fadd((float)px, fx), denx, halfx),
-            grid_roundtrip(fadd((float)py, fy), deny, halfy), H, W);
-  const float* src = x + (size_t)b * C * plane;
-  float* dst = out + (size_t)b * C * plane + rem;
+  if (EXACT_RCP)
+    tap.setup(grid_roundtrip_rcp(fadd((float)px, fx), denx, __frcp_rn(denx), halfx),
+              grid_roundtrip_rcp(fadd((float)py, fy), deny, __frcp_rn(deny), halfy), H, W);
+  else
+    tap.setup(grid_roundtrip(fadd((float)px, fx), denx, halfx),
+              grid_roundtrip(fadd((float)py, fy), deny, halfy), H, W);
+  // two running 64-bit row pointers stepped by the plane stride: one add each per channel
+  const float* pn = x + (size_t)b * C * plane + tap.off_nw;
+  const float* ps = pn + W;
+  float* po = out + (size_t)b * C * plane + rem;
   if (C_T > 0) {
     float v[C_T > 0 ? C_T : 1];
 #pragma unroll
-    for (int c = 0; c < C_T; ++c) v[c] = tap.sample(src + (size_t)c * plane, W);
+    for (int c = 0; c < C_T; ++c) {
+      v[c] = tap.sample_rows(pn, ps);
+      pn += plane; ps += plane;
+    }
     if (C_T == 6 && overlap) {
       // flowHomoAdpater.py:171-174 on the UNMASKED warp: where(mean_c(mask) < 0.9, 1, 0)
       const float mean = fdiv(fadd(fadd(v[3 % C_T], v[4 % C_T]), v[5 % C_T]), 3.0f);
       stg_stream(overlap + (size_t)b * plane + rem, mean < 0.9f ? 1.0f : 0.0f);
     }
 #pragma unroll
-    for (int c = 0; c < C_T; ++c) stg_stream(dst + (size_t)c * plane, mul_mask ? fmul(v[c], m) : v[c]);
+    for (int c = 0; c < C_T; ++c) {
+      stg_stream(po, mul_mask ? fmul(v[c], m) : v[c]);
+      po += plane;
+    }
   } else {
     for (int c = 0; c < C; ++c) {
-      const float v = tap.sample(src + (size_t)c * plane, W);
-      stg_stream(dst + (size_t)c * plane, mul_mask ? fmul(v, m) : v);
+      const float v = tap.sample_rows(pn, ps);
+      stg_stream(po, mul_mask ? fmul(v, m) : v);
+      pn += plane; ps += plane; po += plane;
     }
   }
 }
@@ -73,8 +86,12 @@ extern "C" int sb_flow_warp(const float* x, const float* flo, const float* mul_m
   SB_REQUIRE(B <= 65535 && (H + 7) / 8 <= 65535, SB_EUNSUP, "sb_flow_warp: B or H too large for one launch");
   const dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, B);
   cudaStream_t s = as_stream(stream);
-#define SB_FLOW_LAUNCH(CT) \
-  flow_warp_kernel<CT><<<grid, block, 0, s>>>(x, flo, mul_mask, out, overlap, C, H, W)
+  // the reciprocal restatement of the division by (size-1) is proven for integer sizes up to 2048
+  const int exact_rcp = (W >= 2 && W <= 2048 && H >= 2 && H <= 2048) ? 1 : 0;
+#define SB_FLOW_LAUNCH(CT)   do {                                                                                  \
+    if (exact_rcp) flow_warp_kernel<CT, true><<<grid, block, 0, s>>>(x, flo, mul_mask, out, overlap, C, H, W);  \
+    else flow_warp_kernel<CT, false><<<grid, block, 0, s>>>(x, flo, mul_mask, out, overlap, C, H, W);           \
+  } while (0)
   switch (C) {
     case 1: SB_FLOW_LAUNCH(1); break;
     case 2: SB_FLOW_LAUNCH(2); break;

@@ -185,6 +185,24 @@ int sb_tps_warp(const float* U, const float* T, const float* source,
                 int B, int C, int H, int W, int Hout, int Wout, int pn,
                 sb_stream_t stream);
 
+/* ------------------------------------------------------------------ W3k
+ * Replaces warp_image_tps(image, kernel_centers, kernel_weights, affine_weights, align_corners)
+ * (core/inference/tps_methods/kornia_tps.py:105-176; called from core/inference/tps_pipline.py:381):
+ * dense kornia-style TPS evaluation on create_meshgrid(h, w) followed by
+ * F.grid_sample(bilinear, zeros, align_corners) — fused, the [B, H*W, K] kernel matrix is never
+ * materialised.
+ *   centers, kweights [B,K,2]; affine [B,3,2]; xs [W], ys [H]: the meshgrid tables
+ *   ((linspace(0, n-1, n) / (n-1) - 0.5) * 2, computed by the caller like the reference does);
+ *   out [B,C,H,W]; coords_dbg: optional [B,H,W,2] warped sampling grid (NULL to skip). */
+int sb_tps_kornia_warp(const float* image, const float* centers, const float* kweights,
+                       const float* affine, const float* xs, const float* ys, float* out,
+                       float* coords_dbg, int B, int C, int H, int W, int K, int align_corners,
+                       sb_stream_t stream);
+/* F.grid_sample(img [N,C,H,W], grid [N,Ho,Wo,2], mode='bilinear', padding_mode='zeros',
+ * align_corners) -> out [N,C,Ho,Wo]  (the sampler of kornia_tps.py:172). */
+int sb_grid_sample(const float* img, const float* grid, float* out, int N, int C, int H, int W,
+                   int Ho, int Wo, int align_corners, sb_stream_t stream);
+
 /* ------------------------------------------------------------------ W4
  * Replaces compute_range_map(flow) (core/warp_utils.py:114-175): forward
  * bilinear splat count.  Deterministic: weights are accumulated as 2^-32

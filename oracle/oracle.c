@@ -255,6 +255,62 @@ void o_tps_warp(const float* U, const float* T, const float* source, const float
     }
 }
 
+/* W3k — warp_image_tps (core/inference/tps_methods/kornia_tps.py:105-176) = kornia's
+ * create_meshgrid + warp_points_tps (kornia is absent from the image and unpinned by the
+ * reference: restated from its published source) + F.grid_sample(bilinear, zeros, align_corners):
+ *   d2_k = clamp(-2 p.c_k + |p|^2 + |c_k|^2, 0)   (_pair_square_euclidean :26-36)
+ *   U_k  = 0.5 * d2_k * log(d2_k + 1e-8)          (_kernel_distance :38-45)
+ *   q    = sum_k U_k w_k + (p.x a_1 + p.y a_2) + a_0
+ * torch reduces the K products with a vectorised cascade sum in an unspecified order; the oracle
+ * accumulates them in fp64.  ATen CPU un-normalisation (verified bit-for-bit against
+ * F.grid_sample here): align_corners ? (g + 1) * ((size-1)/2) : fma(g + 1, size/2, -0.5). */
+static inline float gs_unnormalize(float g, int size, int align_corners) {
+  if (align_corners) return (g + 1.0f) * ((float)(size - 1) / 2.0f);
+  return fmaf(g + 1.0f, (float)size / 2.0f, -0.5f);
+}
+
+void o_grid_sample(const float* img, const float* grid, float* out, int N, int C, int H, int W,
+                   int Ho, int Wo, int align_corners) {
+  const i64 plane = (i64)H * W, HoWo = (i64)Ho * Wo;
+#pragma omp parallel for schedule(static)
+  for (i64 p = 0; p < (i64)N * HoWo; ++p) {
+    const i64 n = p / HoWo, rem = p - n * HoWo;
+    gtap_t t;
+    gtap_setup(&t, gs_unnormalize(grid[p * 2], W, align_corners),
+               gs_unnormalize(grid[p * 2 + 1], H, align_corners), H, W);
+    for (int c = 0; c < C; ++c) out[(n * C + c) * HoWo + rem] = gtap_sample(&t, img + (n * C + c) * plane, W);
+  }
+}
+
+void o_tps_kornia_grid(const float* centers, const float* kweights, const float* affine,
+                       const float* xs, const float* ys, float* grid, int B, int H, int W, int K) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int r = 0; r < H; ++r) {
+      const float* cp = centers + (i64)b * K * 2;
+      const float* wp = kweights + (i64)b * K * 2;
+      const float* A = affine + (i64)b * 6;
+      for (int c = 0; c < W; ++c) {
+        const float gx = xs[c], gy = ys[r];
+        const float p2 = gx * gx + gy * gy;
+        double ax = 0.0, ay = 0.0;
+        for (int k = 0; k < K; ++k) {
+          const float cx = cp[2 * k], cy = cp[2 * k + 1];
+          const float c2 = cx * cx + cy * cy;
+          const float dot = gx * cx + gy * cy;
+          float d2 = (-2.0f * dot + p2) + c2;
+          d2 = d2 > 0.0f ? d2 : 0.0f;
+          const float u = (0.5f * d2) * logf(d2 + 1e-8f);
+          ax += (double)wp[2 * k] * (double)u;
+          ay += (double)wp[2 * k + 1] * (double)u;
+        }
+        float* g = grid + (((i64)b * H + r) * W + c) * 2;
+        g[0] = ((float)ax + (gx * A[2] + gy * A[4])) + A[0];
+        g[1] = ((float)ay + (gx * A[3] + gy * A[5])) + A[1];
+      }
+    }
+}
+
 /* W4 — compute_range_map: core/warp_utils.py:114-175, and the 'wang' branch of
  * compute_occlusion (:185-221).  scatter_add_ on the CPU adds the weights in
  * list order: (di, dj) outer (:142-143), flattened [B,H,W] pixels inner.

@@ -197,6 +197,43 @@ def tps_transformer(U, source, target, out_size, return_indices=False, return_co
     return res[0] if len(res) == 1 else tuple(res)
 
 
+# ----------------------------------------------------------------- W3k
+def kornia_axis_table(n):
+    """create_meshgrid's normalised axis: (linspace(0, n-1, n) / (n-1) - 0.5) * 2, taken from torch."""
+    import torch
+    t = torch.linspace(0, n - 1, n)
+    return ((t / (n - 1) - 0.5) * 2).numpy().copy()
+
+
+def grid_sample(img, grid, align_corners=False):
+    """F.grid_sample(img, grid, 'bilinear', 'zeros', align_corners) (kornia_tps.py:172)."""
+    im, gr = _f32(img), _f32(grid)
+    n, c, h, w = im.shape
+    ho, wo = gr.shape[1], gr.shape[2]
+    out = np.empty((n, c, ho, wo), np.float32)
+    _load().o_grid_sample(_p(im), _p(gr), _p(out), c_int(n), c_int(c), c_int(h), c_int(w), c_int(ho), c_int(wo),
+                          c_int(1 if align_corners else 0))
+    return out
+
+
+def tps_kornia_grid(kernel_centers, kernel_weights, affine_weights, h, w):
+    """warp_points_tps on create_meshgrid(h, w): the sampling grid [B,H,W,2] of warp_image_tps."""
+    kc, kw, aw = _f32(kernel_centers), _f32(kernel_weights), _f32(affine_weights)
+    b, k, _ = kc.shape
+    xs, ys = kornia_axis_table(w), kornia_axis_table(h)
+    grid = np.empty((b, h, w, 2), np.float32)
+    _load().o_tps_kornia_grid(_p(kc), _p(kw), _p(aw), _p(xs), _p(ys), _p(grid), c_int(b), c_int(h), c_int(w), c_int(k))
+    return grid
+
+
+def warp_image_tps(image, kernel_centers, kernel_weights, affine_weights, align_corners=False, return_grid=False):
+    """kornia_tps.py:105-176."""
+    im = _f32(image)
+    grid = tps_kornia_grid(kernel_centers, kernel_weights, affine_weights, im.shape[2], im.shape[3])
+    out = grid_sample(im, grid, align_corners)
+    return (out, grid) if return_grid else out
+
+
 # ----------------------------------------------------------------- W4 / W5
 def _range(flow, mode):
     fl = _f32(flow)

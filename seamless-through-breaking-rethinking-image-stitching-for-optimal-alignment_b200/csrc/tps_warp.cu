@@ -78,7 +78,159 @@ tps_warp_kernel(const float* __restrict__ U, const float* __restrict__ T,
   }
 }
 
+// ---------------------------------------------------------------------------
+// W3k: kornia-style TPS image warp, warp_image_tps(image, kernel_centers, kernel_weights,
+// affine_weights, align_corners) (core/inference/tps_methods/kornia_tps.py:105-176):
+//   coords  = create_meshgrid(h, w) in [-1, 1]                       (tables xs / ys passed in)
+//   d2_k    = clamp(-2 * p.c_k + |p|^2 + |c_k|^2, min=0)             (_pair_square_euclidean :26-36)
+//   U_k     = 0.5 * d2_k * log(d2_k + 1e-8)                          (_kernel_distance :38-45)
+//   warped  = sum_k U_k * w_k + (p.x * a_1 + p.y * a_2) + a_0        (kornia warp_points_tps)
+//   out     = F.grid_sample(image, warped, bilinear, zeros, align_corners)   (:170-174)
+// Same structure as the kernel above: the [B, H*W, K] kernel matrix is never materialised, the
+// sum over control points is accumulated in fp64 (order-independent), FP32-ALU / MUFU bound.
+template <int C_T>
+__global__ void __launch_bounds__(256)
+tps_kornia_warp_kernel(const float* __restrict__ image, const float* __restrict__ centers,
+                       const float* __restrict__ kweights, const float* __restrict__ affine,
+                       const float* __restrict__ xs, const float* __restrict__ ys,
+                       float* __restrict__ out, float* __restrict__ coords_dbg, int C_rt, int H, int W,
+                       int K, int align_corners, int blocks_per_image) {
+  extern __shared__ float s_tps[];  // cx[K], cy[K], c2[K], wx[K], wy[K]
+  float* s_cx = s_tps;
+  float* s_cy = s_cx + K;
+  float* s_c2 = s_cy + K;
+  float* s_wx = s_c2 + K;
+  float* s_wy = s_wx + K;
+  const int C = (C_T > 0) ? C_T : C_rt;
+  const int b = blockIdx.x / blocks_per_image;
+  const int blk = blockIdx.x - b * blocks_per_image;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float cx = __ldg(centers + ((long long)b * K + k) * 2), cy = __ldg(centers + ((long long)b * K + k) * 2 + 1);
+    s_cx[k] = cx; s_cy[k] = cy;
+    s_c2[k] = fadd(fmul(cx, cx), fmul(cy, cy));                     // t2_sq = sum(c * c)
+    s_wx[k] = __ldg(kweights + ((long long)b * K + k) * 2);
+    s_wy[k] = __ldg(kweights + ((long long)b * K + k) * 2 + 1);
+  }
+  __syncthreads();
+  const float* A = affine + (long long)b * 6;                       // [3, 2]: rows a_0, a_1 (x), a_2 (y)
+  const float a0x = __ldg(A), a0y = __ldg(A + 1), a1x = __ldg(A + 2), a1y = __ldg(A + 3),
+              a2x = __ldg(A + 4), a2y = __ldg(A + 5);
+  const long long plane = (long long)H * W;
+  // ATen CPU grid_sample: align_corners ? (g + 1) * ((size-1)/2) : fma(g + 1, size/2, -0.5)
+  const float sfx = align_corners ? fmul((float)(W - 1), 0.5f) : fmul((float)W, 0.5f);
+  const float sfy = align_corners ? fmul((float)(H - 1), 0.5f) : fmul((float)H, 0.5f);
+  for (long long rem = (long long)blk * blockDim.x + threadIdx.x; rem < plane;
+       rem += (long long)blocks_per_image * blockDim.x) {
+    const int r = (int)(rem / W), c = (int)(rem - (long long)r * W);
+    const float gx = __ldg(xs + c), gy = __ldg(ys + r);
+    const float p2 = fadd(fmul(gx, gx), fmul(gy, gy));              // t1_sq
+    double ax = 0.0, ay = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float dot = fadd(fmul(gx, s_cx[k]), fmul(gy, s_cy[k]));
+      float d2 = fadd(fadd(fmul(-2.0f, dot), p2), s_c2[k]);
+      d2 = fmaxf(d2, 0.0f);
+      const float u = fmul(fmul(0.5f, d2), logf(fadd(d2, 1e-8f)));
+      ax = fma((double)s_wx[k], (double)u, ax);
+      ay = fma((double)s_wy[k], (double)u, ay);
+    }
+    // + points . affine[1:] + affine[0]
+    const float wxs = fadd(fadd((float)ax, fadd(fmul(gx, a1x), fmul(gy, a2x))), a0x);
+    const float wys = fadd(fadd((float)ay, fadd(fmul(gx, a1y), fmul(gy, a2y))), a0y);
+    if (coords_dbg) {
+      coords_dbg[((long long)b * plane + rem) * 2] = wxs;
+      coords_dbg[((long long)b * plane + rem) * 2 + 1] = wys;
+    }
+    const float ix = align_corners ? fmul(fadd(wxs, 1.0f), sfx) : __fmaf_rn(fadd(wxs, 1.0f), sfx, -0.5f);
+    const float iy = align_corners ? fmul(fadd(wys, 1.0f), sfy) : __fmaf_rn(fadd(wys, 1.0f), sfy, -0.5f);
+    GridTap tap;
+    tap.setup(ix, iy, H, W);
+    const float* src = image + (long long)b * C * plane;
+    float* dst = out + (long long)b * C * plane + rem;
+    if (C_T > 0) {
+      float v[C_T > 0 ? C_T : 1];
+#pragma unroll
+      for (int ch = 0; ch < C_T; ++ch) v[ch] = tap.sample(src + ch * plane, W);
+#pragma unroll
+      for (int ch = 0; ch < C_T; ++ch) stg_stream(dst + ch * plane, v[ch]);
+    } else {
+      for (int ch = 0; ch < C; ++ch) stg_stream(dst + ch * plane, tap.sample(src + ch * plane, W));
+    }
+  }
+}
+
+// Plain F.grid_sample(bilinear, zeros) on a normalised grid [N, Ho, Wo, 2], both align_corners modes.
+__global__ void __launch_bounds__(256)
+grid_sample_kernel(const float* __restrict__ img, const float* __restrict__ grid, float* __restrict__ out,
+                   int C, int H, int W, long long HoWo, long long total, int align_corners) {
+  const float sfx = align_corners ? fmul((float)(W - 1), 0.5f) : fmul((float)W, 0.5f);
+  const float sfy = align_corners ? fmul((float)(H - 1), 0.5f) : fmul((float)H, 0.5f);
+  const long long plane = (long long)H * W;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / HoWo, rem = p - n * HoWo;
+    const float gx = __ldg(grid + p * 2), gy = __ldg(grid + p * 2 + 1);
+    const float ix = align_corners ? fmul(fadd(gx, 1.0f), sfx) : __fmaf_rn(fadd(gx, 1.0f), sfx, -0.5f);
+    const float iy = align_corners ? fmul(fadd(gy, 1.0f), sfy) : __fmaf_rn(fadd(gy, 1.0f), sfy, -0.5f);
+    GridTap tap;
+    tap.setup(ix, iy, H, W);
+    for (int c = 0; c < C; ++c) out[(n * C + c) * HoWo + rem] = tap.sample(img + (n * C + c) * plane, W);
+  }
+}
+
 }  // namespace sb
+
+extern "C" int sb_tps_kornia_warp(const float* image, const float* centers, const float* kweights,
+                                  const float* affine, const float* xs, const float* ys, float* out,
+                                  float* coords_dbg, int B, int C, int H, int W, int K,
+                                  int align_corners, sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(B >= 0 && C >= 0 && H > 0 && W > 0 && K >= 0, SB_EINVAL, "sb_tps_kornia_warp: bad size");
+  SB_REQUIRE(K <= kTpsMaxPn, SB_EUNSUP, "sb_tps_kornia_warp: K=%d > %d control points", K, kTpsMaxPn);
+  SB_REQUIRE((long long)H * W < (1ll << 31), SB_EUNSUP, "sb_tps_kornia_warp: plane too large");
+  const long long plane = (long long)H * W;
+  if ((long long)B * plane == 0 || C == 0) return SB_OK;
+  SB_REQUIRE(image && centers && kweights && affine && xs && ys && out, SB_EINVAL,
+             "sb_tps_kornia_warp: null pointer");
+  const int threads = 256;
+  long long bpi = (plane + threads - 1) / threads;
+  const long long cap = (long long)kNumSMs * 8 * 4 / (B > 0 ? B : 1) + 1;
+  if (bpi > cap) bpi = cap;
+  const size_t smem = (size_t)(5 * K) * sizeof(float);
+  const int grid = (int)(bpi * B);
+  cudaStream_t s = as_stream(stream);
+#define SB_TPSK_LAUNCH(CT)                                                                          \
+  tps_kornia_warp_kernel<CT><<<grid, threads, smem, s>>>(image, centers, kweights, affine, xs, ys, \
+                                                         out, coords_dbg, C, H, W, K, align_corners, (int)bpi)
+  switch (C) {
+    case 1: SB_TPSK_LAUNCH(1); break;
+    case 3: SB_TPSK_LAUNCH(3); break;
+    case 6: SB_TPSK_LAUNCH(6); break;
+    default: SB_TPSK_LAUNCH(0); break;
+  }
+#undef SB_TPSK_LAUNCH
+  SB_LAUNCH_CHECK("tps_kornia_warp_kernel");
+  return SB_OK;
+}
+
+extern "C" int sb_grid_sample(const float* img, const float* grid, float* out, int N, int C, int H, int W,
+                              int Ho, int Wo, int align_corners, sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(N >= 0 && C >= 0 && H > 0 && W > 0 && Ho >= 0 && Wo >= 0, SB_EINVAL, "sb_grid_sample: bad size");
+  SB_REQUIRE((long long)H * W < (1ll << 31), SB_EUNSUP, "sb_grid_sample: plane too large");
+  const long long HoWo = (long long)Ho * Wo, total = (long long)N * HoWo;
+  if (total == 0 || C == 0) return SB_OK;
+  SB_REQUIRE(img && grid && out, SB_EINVAL, "sb_grid_sample: null pointer");
+  long long blocks = (total + 255) / 256;
+  const long long max_blocks = (long long)kNumSMs * 8 * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  grid_sample_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(img, grid, out, C, H, W, HoWo, total,
+                                                                 align_corners);
+  SB_LAUNCH_CHECK("grid_sample_kernel");
+  return SB_OK;
+}
 
 extern "C" int sb_tps_warp(const float* U, const float* T, const float* source, const float* xs,
                            const float* ys, float* out, int32_t* idx_dbg, int B, int C, int H,

@@ -149,6 +149,21 @@ def tps_small():
     return dict(U=base[None].repeat(b, 1, 1, 1).contiguous(), source=src, target=tgt, out_size=(32, 40))
 
 
+# ------------------------------------------------------------------ W3k
+def tps_kornia_small():
+    """warp_image_tps inputs as tps_pipline.py:364-381 builds them: control points in pixels
+    divided by the canvas size (so in [0,1]), reverse transform dst -> src."""
+    g = _g(45)
+    b, gh, gw, h, w = 2, 5, 5, 36, 44
+    ys, xs = torch.meshgrid(torch.linspace(0.05, 0.95, gh), torch.linspace(0.05, 0.95, gw), indexing="ij")
+    src = torch.stack([xs, ys], -1).reshape(1, -1, 2).repeat(b, 1, 1)
+    dst = src + 0.02 * torch.randn(b, gh * gw, 2, generator=g)
+    yy, xx = torch.meshgrid(torch.linspace(0, 3.0, h), torch.linspace(0, 4.0, w), indexing="ij")
+    base = torch.stack([torch.sin(xx) + yy, torch.cos(yy * 1.3) * 2, xx * yy * 0.3, torch.ones_like(xx),
+                        torch.ones_like(xx), torch.ones_like(xx)], 0)
+    return dict(image=base[None].repeat(b, 1, 1, 1).contiguous(), points_src=src, points_dst=dst)
+
+
 # ------------------------------------------------------------------ W4 / W5
 def range_small():
     g = _g(50)

@@ -193,6 +193,42 @@ def main():
     r = ref_build_model(lambda *a: c["net_out"], c["warp1"], c["warp2"], c["mask1"], c["mask2"])
     save("build_model", cases.checksum(*c.values()), **{k: v.numpy() for k, v in r.items()})
 
+    # ---------------------------------------------------------------- W3k (kornia absent: the two
+    # functions the reference imports from it are restated from kornia's published source in a stub
+    # module; everything else — _pair_square_euclidean, _kernel_distance, custom_get_tps_transform,
+    # warp_image_tps — is the reference's own vendored code in core/inference/tps_methods/kornia_tps.py)
+    def _k_warp_points_tps(points_src, kernel_centers, kernel_weights, affine_weights):
+        pair = ref_ktps._pair_square_euclidean(points_src, kernel_centers)
+        k_matrix = ref_ktps._kernel_distance(pair)
+        return (k_matrix[..., None].mul(kernel_weights[:, None]).sum(-2)
+                + points_src[..., None].mul(affine_weights[:, None, 1:]).sum(-2)
+                + affine_weights[:, None, 0])
+
+    def _k_create_meshgrid(height, width, normalized_coordinates=True, device=None, dtype=torch.float32):
+        xs = torch.linspace(0, width - 1, width, device=device, dtype=dtype)
+        ys = torch.linspace(0, height - 1, height, device=device, dtype=dtype)
+        if normalized_coordinates:
+            xs = (xs / (width - 1) - 0.5) * 2
+            ys = (ys / (height - 1) - 0.5) * 2
+        return torch.stack(torch.meshgrid([xs, ys], indexing="ij"), dim=-1).permute(1, 0, 2).unsqueeze(0)
+
+    for name in ("kornia", "kornia.geometry", "kornia.geometry.transform", "kornia.utils", "kornia.core"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    kt = sys.modules["kornia.geometry.transform"]
+    kt.warp_image_tps = kt.get_tps_transform = None          # shadowed by the reference's own definitions
+    kt.warp_points_tps = _k_warp_points_tps
+    sys.modules["kornia.utils"].create_meshgrid = _k_create_meshgrid
+    sys.modules["kornia.core"].Tensor = torch.Tensor
+    import core.inference.tps_methods.kornia_tps as ref_ktps
+    c = cases.tps_kornia_small()
+    kwt, awt = ref_ktps.custom_get_tps_transform(c["points_dst"], c["points_src"])
+    arrays = dict(kernel_weights=kwt.numpy(), affine_weights=awt.numpy())
+    for ac in (False, True):
+        arrays[f"out_ac{int(ac)}"] = ref_ktps.warp_image_tps(c["image"], c["points_src"], kwt, awt, align_corners=ac).numpy()
+    coords = _k_create_meshgrid(c["image"].shape[2], c["image"].shape[3]).reshape(-1, 2).expand(c["image"].shape[0], -1, -1)
+    arrays["grid"] = _k_warp_points_tps(coords, c["points_src"], kwt, awt).view(-1, c["image"].shape[2], c["image"].shape[3], 2).numpy()
+    save("tps_kornia", cases.checksum(*c.values()), **arrays)
+
     # ---------------------------------------------------------------- W8 (restated: tps_pipline.py needs matplotlib
     # + cv2-contrib at import/run time; lines :139-170 are restated here with the same torch / cv2 calls)
     import cv2

@@ -323,6 +323,42 @@ def test_tps_169_points_vs_oracle(sb):
     assert max_abs(np.where(ok, host(out), 0), np.where(ok, ref, 0)) <= 1e-3
 
 
+# ===================================================================== W3k
+def test_tps_kornia_golden(sb):
+    c = cases.tps_kornia_small()
+    g = golden("tps_kornia")
+    check_inputs(g, *c.values())
+    kt = sb.kornia_tps
+    img = cu(c["image"])
+    for ac in (False, True):
+        # the sampler alone, on the reference's own grid: bit-exact
+        assert_bits_equal(host(kt.grid_sample(img, cu(g["grid"]), align_corners=ac)), g[f"out_ac{int(ac)}"],
+                          f"grid_sample align_corners={ac}")
+        out, grid = kt.warp_image_tps(img, cu(c["points_src"]), cu(g["kernel_weights"]), cu(g["affine_weights"]),
+                                      align_corners=ac, return_grid=True)
+        assert max_abs(host(grid), g["grid"]) <= 5e-6                       # fp64-accumulated K-term sum
+        assert_bits_equal(host(out), host(kt.grid_sample(img, grid, align_corners=ac)), "fused == grid + sample")
+        assert_bits_equal(host(out), so.grid_sample(c["image"].numpy(), host(grid), ac), "sampler vs oracle")
+        assert max_abs(host(out), g[f"out_ac{int(ac)}"]) <= 1e-3            # the stated contract
+    # the solve (pseudo-inverse, GPU vs CPU LAPACK) agrees to the conditioning of the system
+    kw, aw = kt.get_tps_transform(cu(c["points_dst"]), cu(c["points_src"]))
+    out = kt.warp_image_tps(img, cu(c["points_src"]), kw, aw)
+    assert max_abs(host(out), g["out_ac0"]) <= 5e-2
+
+
+def test_tps_kornia_169_points_vs_oracle(sb):
+    g = torch.Generator().manual_seed(46)
+    ys, xs = torch.meshgrid(torch.linspace(0.02, 0.98, 13), torch.linspace(0.02, 0.98, 13), indexing="ij")
+    src = torch.stack([xs, ys], -1).reshape(1, -1, 2).repeat(2, 1, 1)
+    kw = 0.01 * torch.randn(2, 169, 2, generator=g)
+    aw = torch.tensor([[0.01, -0.02], [1.0, 0.01], [-0.01, 1.0]]).repeat(2, 1, 1) + 0.01 * torch.randn(2, 3, 2, generator=g)
+    img = torch.rand(2, 6, 200, 264, generator=g) * 255.0
+    out, grid = sb.kornia_tps.warp_image_tps(cu(img), cu(src), cu(kw), cu(aw), return_grid=True)
+    rgrid = so.tps_kornia_grid(src.numpy(), kw.numpy(), aw.numpy(), 200, 264)
+    assert max_abs(host(grid), rgrid) <= 5e-6
+    assert_bits_equal(host(out), so.grid_sample(img.numpy(), host(grid), False), "sampler vs oracle on the kernel's grid")
+
+
 # ===================================================================== W4
 def _occ_compare(got, ref_raw, what):
     """Thresholded masks are bit-exact except where the reference's own fp32 value sits

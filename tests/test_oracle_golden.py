@@ -126,6 +126,25 @@ def test_tps():
     assert max_abs(np.where(ok, out, 0), np.where(ok, g["out"], 0)) <= 1e-3
 
 
+# ---------------------------------------------------------------- W3k
+def test_tps_kornia():
+    """warp_image_tps of the reference's kornia_tps.py (warp_points_tps / create_meshgrid restated
+    from kornia, which is absent and unpinned: 'pinned modulo that restatement')."""
+    c = cases.tps_kornia_small()
+    g = golden("tps_kornia")
+    check_inputs(g, *c.values())
+    img = c["image"].numpy()
+    # the sampler is pinned exactly: reference grid -> reference output, both align_corners modes
+    for ac in (0, 1):
+        assert_bits_equal(so.grid_sample(img, g["grid"], bool(ac)), g[f"out_ac{ac}"], f"grid_sample align_corners={ac}")
+    # the K-term fp32 sum of the reference is order-unspecified (torch cascade sum): grid to ~1e-6
+    grid = so.tps_kornia_grid(c["points_src"].numpy(), g["kernel_weights"], g["affine_weights"], img.shape[2], img.shape[3])
+    assert max_abs(grid, g["grid"]) <= 5e-6
+    for ac in (0, 1):
+        out = so.warp_image_tps(img, c["points_src"].numpy(), g["kernel_weights"], g["affine_weights"], bool(ac))
+        assert max_abs(out, g[f"out_ac{ac}"]) <= 1e-3
+
+
 # ---------------------------------------------------------------- W4
 @pytest.mark.parametrize("name", ["range_small", "range_smooth"])
 def test_range_map(name):

@@ -180,7 +180,7 @@ def run_ours(args):
     # rank r owns pairs [r*B, (r+1)*B) of the global list (weak scaling, no data-path collective)
     pb_host = make_pair_batch(rank * B, B, size=SIZE, iters=ITERS).map(lambda t: t.pin_memory())
     pb_dev = pb_host.map(lambda t: t.to(dev, non_blocking=True))
-    hp = HotPath(size=SIZE, iters=ITERS, pyramid=True)
+    hp = HotPath(size=SIZE, iters=ITERS, pyramid=True, overlap=args.overlap)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -333,7 +333,8 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(world), "global_batch": B * world, "image_size": SIZE,
-                       "lookup_iters": ITERS, "submission": "cuda-graph replay" if args.graph else "eager launches",
+                       "lookup_iters": ITERS, "submission": ("cuda-graph replay" if args.graph else "eager launches") +
+                       (", warp stage on a second stream (fork/join)" if args.overlap else ""),
                        "parallelism": f"pairs sharded x{world}, no data-path collective",
                        "l2": "per-step working set (2 x 1 GiB volumes) >> 126 MB L2, no explicit flush",
                        "algorithmic_bytes_per_step": work["bytes"], "algorithmic_flops_per_step": work["flops"]},
@@ -371,7 +372,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="eager launches instead of replaying the step as one captured CUDA graph")
-    ap.set_defaults(graph=True)
+    ap.add_argument("--no-overlap", dest="overlap", action="store_false",
+                    help="run the warp stage after the cost-volume stage instead of on a second stream")
+    ap.set_defaults(graph=True, overlap=True)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

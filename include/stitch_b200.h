@@ -59,6 +59,7 @@ enum {
   SB_TUNE_LOOKUP_CTAS_PER_SM = 1,  /* resident CTAs per SM the persistent lookup grid is sized for */
   SB_TUNE_LOOKUP_SUPERBLOCK = 2,   /* queries per superblock: 8, 16 or 32 (default: by problem size) */
   SB_TUNE_LOOKUP_FETCH_ONLY = 3,   /* EXPERIMENT ONLY (changes results): windows are fetched, taps are not sampled */
+  SB_TUNE_LOOKUP_L2_KEEP_EIGHTHS = 4, /* n/8 of the window fetches carry an L2 evict_last policy (default 3; 15 = no hint) */
   SB_TUNE_COUNT = 16
 };
 int sb_tune(int key, int value);

@@ -235,6 +235,8 @@ corr_lookup_r4_kernel(const __grid_constant__ LookupMaps maps, const float* __re
 
   const int sbq_flags = sbq;
   sbq &= 0xff;
+  const int l2_eighths = ((sbq_flags >> 12) & 0xf) <= 8 ? (sbq_flags >> 12) & 0xf : 0;   // 0 = no cache hint
+  const uint64_t l2_policy = l2_eighths > 0 ? ptx::l2_policy_evict_last_fraction(l2_eighths) : 0ull;
   const int gps = sbq / kFastQ;                                   // groups per superblock (>= kFastDepth)
   const int sb_per_b = (HW1 + sbq - 1) / sbq;
   const int n_sb = B * sb_per_b;
@@ -321,7 +323,11 @@ corr_lookup_r4_kernel(const __grid_constant__ LookupMaps maps, const float* __re
         for (int k = 0; k < kFastQ; ++k) {
           if (k < nvalid && over[k] == 0u) {
             const int wide = (big[k] & 0x1ffu) ? 1 : 0, tall = (big[k] >> kFastSide) ? 1 : 0;
-            ptx::tma_load_3d(gbuf_u32 + k * kWinBytes, &maps.m[wide + 2 * tall], bar, ax[k], ymin[k], q0 + k);
+            if (l2_eighths > 0)
+              ptx::tma_load_3d_hint(gbuf_u32 + k * kWinBytes, &maps.m[wide + 2 * tall], bar, ax[k], ymin[k], q0 + k,
+                                    l2_policy);
+            else
+              ptx::tma_load_3d(gbuf_u32 + k * kWinBytes, &maps.m[wide + 2 * tall], bar, ax[k], ymin[k], q0 + k);
             tx += (wide ? 16 : 12) * (tall ? 12 : 10) * 4;
           }
         }
@@ -520,7 +526,8 @@ extern "C" int sb_corr_lookup(const float* cost_maps, const float* coords, float
       long long ctas = n_sb < (long long)kNumSMs * per_sm ? n_sb : (long long)kNumSMs * per_sm;      \
       corr_lookup_r4_kernel<D><<<(int)ctas, kLookupWarps * 32, fast_smem_bytes(D), as_stream(stream)>>>( \
           maps, cost_maps, coords, out, B, hw1, H2, W2, coord_scale, out_stride, out_offset, vec_out, \
-          sbq | (tune_get(SB_TUNE_LOOKUP_FETCH_ONLY, 0) ? 0x100 : 0), dbg_word);                                                                            \
+          sbq | (tune_get(SB_TUNE_LOOKUP_FETCH_ONLY, 0) ? 0x100 : 0) |                              \
+              ((tune_get(SB_TUNE_LOOKUP_L2_KEEP_EIGHTHS, 3) & 0xf) << 12), dbg_word);                                                                            \
     } while (0)
     if (depth == 1) SB_LAUNCH_R4(1);
     else SB_LAUNCH_R4(2);

@@ -70,6 +70,31 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap,
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// same, with an L2 cache-policy operand (createpolicy)
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t smem_dst, const void* tmap, uint32_t bar,
+                                                 int c0, int c1, int c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+        "l"(policy)
+      : "memory");
+}
+// L2 policy: `eighths`/8 of the accesses are kept with evict_last priority, the rest evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last_fraction(int eighths) {
+  uint64_t p;
+  switch (eighths) {
+    case 1: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.125;" : "=l"(p)); break;
+    case 2: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.25;" : "=l"(p)); break;
+    case 3: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.375;" : "=l"(p)); break;
+    case 4: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.5;" : "=l"(p)); break;
+    case 5: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.625;" : "=l"(p)); break;
+    case 6: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.75;" : "=l"(p)); break;
+    case 7: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.875;" : "=l"(p)); break;
+    default: asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); break;
+  }
+  return p;
+}
 __device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1,
                                              int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"

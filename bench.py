@@ -240,7 +240,6 @@ def run_ours(args):
         barrier()
         gemm_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(n_rep)]
         ms_eager_total = None
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,6 +293,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = pairs_total / (t.item() / 1000.0)
     out = last_out()
+    # clocks were sampled from before the device-resident timed region to after the end-to-end one
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- the single collective of the path: final metric reduction
     # (computed from the results that arrived in pinned HOST memory)

@@ -204,6 +204,14 @@ int sb_tps_kornia_warp(const float* image, const float* centers, const float* kw
 int sb_grid_sample(const float* img, const float* grid, float* out, int N, int C, int H, int W,
                    int Ho, int Wo, int align_corners, sb_stream_t stream);
 
+/* ------------------------------------------------------------------ N2 ("next" row 2)
+ * Replaces MemoryDecoder.upsample_flow(flow, mask)
+ * (core/FlowFormer/PerCostFormer3/decoder.py:214-225, called every GRU iteration at :331):
+ * convex 8x upsampling, softmax over the 9 taps of mask [N, 576, H, W] (viewed [N,1,9,8,8,H,W])
+ * applied to the 3x3 zero-padded neighbourhood of 8 * flow [N, 2, H, W] -> out [N, 2, 8H, 8W]. */
+int sb_upsample_flow(const float* flow, const float* mask, float* out, int N, int H, int W,
+                     sb_stream_t stream);
+
 /* ------------------------------------------------------------------ W4
  * Replaces compute_range_map(flow) (core/warp_utils.py:114-175): forward
  * bilinear splat count.  Deterministic: weights are accumulated as 2^-32

@@ -311,6 +311,41 @@ void o_tps_kornia_grid(const float* centers, const float* kweights, const float*
     }
 }
 
+/* N2 — MemoryDecoder.upsample_flow: core/FlowFormer/PerCostFormer3/decoder.py:214-225.
+ * softmax over the 9 taps (ATen, non-last dim: max, exp(x - max), running sum, divide), then
+ * sum_k p_k * (8 * flow)[neighbour k] in tap order (torch.sum over a 9-long dim). */
+void o_upsample_flow(const float* flow, const float* mask, float* out, int N, int H, int W) {
+  const i64 plane = (i64)H * W;
+  const int Ho = 8 * H, Wo = 8 * W;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int n = 0; n < N; ++n)
+    for (int h = 0; h < H; ++h)
+      for (int w = 0; w < W; ++w) {
+        float f[2][9];
+        for (int c = 0; c < 2; ++c)
+          for (int k = 0; k < 9; ++k) {
+            const int hy = h + k / 3 - 1, wx = w + k % 3 - 1;
+            const int ok = hy >= 0 && hy < H && wx >= 0 && wx < W;
+            f[c][k] = ok ? 8.0f * flow[((i64)n * 2 + c) * plane + (i64)hy * W + wx] : 0.0f;
+          }
+        for (int dy = 0; dy < 8; ++dy)
+          for (int dx = 0; dx < 8; ++dx) {
+            float m[9], e[9], mx, sum = 0.0f, a0 = 0.0f, a1 = 0.0f;
+            for (int k = 0; k < 9; ++k) m[k] = mask[((i64)n * 576 + k * 64 + dy * 8 + dx) * plane + (i64)h * W + w];
+            mx = m[0];
+            for (int k = 1; k < 9; ++k) mx = m[k] > mx ? m[k] : mx;
+            for (int k = 0; k < 9; ++k) { e[k] = expf(m[k] - mx); sum += e[k]; }
+            for (int k = 0; k < 9; ++k) {
+              const float p = e[k] / sum;
+              a0 += p * f[0][k];
+              a1 += p * f[1][k];
+            }
+            out[(((i64)n * 2 + 0) * Ho + 8 * h + dy) * Wo + 8 * w + dx] = a0;
+            out[(((i64)n * 2 + 1) * Ho + 8 * h + dy) * Wo + 8 * w + dx] = a1;
+          }
+      }
+}
+
 /* W4 — compute_range_map: core/warp_utils.py:114-175, and the 'wang' branch of
  * compute_occlusion (:185-221).  scatter_add_ on the CPU adds the weights in
  * list order: (di, dj) outer (:142-143), flattened [B,H,W] pixels inner.

@@ -197,6 +197,16 @@ def tps_transformer(U, source, target, out_size, return_indices=False, return_co
     return res[0] if len(res) == 1 else tuple(res)
 
 
+# ----------------------------------------------------------------- N2
+def upsample_flow(flow, mask):
+    """MemoryDecoder.upsample_flow (decoder.py:214-225)."""
+    fl, mk = _f32(flow), _f32(mask)
+    n, _, h, w = fl.shape
+    out = np.empty((n, 2, 8 * h, 8 * w), np.float32)
+    _load().o_upsample_flow(_p(fl), _p(mk), _p(out), c_int(n), c_int(h), c_int(w))
+    return out
+
+
 # ----------------------------------------------------------------- W3k
 def kornia_axis_table(n):
     """create_meshgrid's normalised axis: (linspace(0, n-1, n) / (n-1) - 0.5) * 2, taken from torch."""

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sb_tps_warp": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_tps_kornia_warp": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_grid_sample": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sb_upsample_flow": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "sb_range_map": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_morph_open": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_composite_test_out": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),

@@ -149,6 +149,12 @@ def tps_small():
     return dict(U=base[None].repeat(b, 1, 1, 1).contiguous(), source=src, target=tgt, out_size=(32, 40))
 
 
+# ------------------------------------------------------------------ N2
+def upsample_small():
+    g = _g(60)
+    return dict(flow=torch.randn(2, 2, 12, 20, generator=g) * 3.0, mask=torch.randn(2, 576, 12, 20, generator=g) * 2.0)
+
+
 # ------------------------------------------------------------------ W3k
 def tps_kornia_small():
     """warp_image_tps inputs as tps_pipline.py:364-381 builds them: control points in pixels

@@ -193,6 +193,10 @@ def main():
     r = ref_build_model(lambda *a: c["net_out"], c["warp1"], c["warp2"], c["mask1"], c["mask2"])
     save("build_model", cases.checksum(*c.values()), **{k: v.numpy() for k, v in r.items()})
 
+    # ---------------------------------------------------------------- N2
+    c = cases.upsample_small()
+    save("upsample_small", cases.checksum(*c.values()), out=MemoryDecoder.upsample_flow(None, c["flow"], c["mask"]).numpy())
+
     # ---------------------------------------------------------------- W3k (kornia absent: the two
     # functions the reference imports from it are restated from kornia's published source in a stub
     # module; everything else — _pair_square_euclidean, _kernel_distance, custom_get_tps_transform,

@@ -323,6 +323,36 @@ def test_tps_169_points_vs_oracle(sb):
     assert max_abs(np.where(ok, host(out), 0), np.where(ok, ref, 0)) <= 1e-3
 
 
+# ===================================================================== N2 (next row 2)
+def test_upsample_flow_golden(sb):
+    c = cases.upsample_small()
+    g = golden("upsample_small")
+    check_inputs(g, *c.values())
+    out = host(sb.decoder.upsample_flow(cu(c["flow"]), cu(c["mask"])))
+    assert out.shape == g["out"].shape
+    assert max_abs(out, g["out"]) <= 3e-5
+    assert max_abs(out, so.upsample_flow(c["flow"].numpy(), c["mask"].numpy())) <= 3e-5
+
+
+def test_upsample_flow_full_size_and_properties(sb):
+    gen = torch.Generator().manual_seed(61)
+    flow = torch.randn(2, 2, 64, 64, generator=gen) * 4.0
+    mask = torch.randn(2, 576, 64, 64, generator=gen)
+    out = host(sb.decoder.upsample_flow(cu(flow), cu(mask)))
+    assert max_abs(out, so.upsample_flow(flow.numpy(), mask.numpy())) <= 3e-5
+    # a mask that puts all weight on the centre tap (k = 4) reproduces 8 * flow, nearest-upsampled, exactly
+    onehot = torch.full((2, 576, 64, 64), -1e4)
+    onehot[:, 4 * 64:5 * 64] = 0.0
+    out = host(sb.decoder.upsample_flow(cu(flow), cu(onehot)))
+    ref = (8.0 * flow).repeat_interleave(8, dim=2).repeat_interleave(8, dim=3).numpy()
+    assert_bits_equal(out, ref, "centre-tap mask == 8 * flow upsampled")
+    # ragged width (not a multiple of the 32-pixel CTA tile) and a single row
+    flow = torch.randn(1, 2, 1, 45, generator=gen)
+    mask = torch.randn(1, 576, 1, 45, generator=gen)
+    out = host(sb.decoder.upsample_flow(cu(flow), cu(mask)))
+    assert max_abs(out, so.upsample_flow(flow.numpy(), mask.numpy())) <= 3e-5
+
+
 # ===================================================================== W3k
 def test_tps_kornia_golden(sb):
     c = cases.tps_kornia_small()

@@ -126,6 +126,17 @@ def test_tps():
     assert max_abs(np.where(ok, out, 0), np.where(ok, g["out"], 0)) <= 1e-3
 
 
+# ---------------------------------------------------------------- N2
+def test_upsample_flow():
+    c = cases.upsample_small()
+    g = golden("upsample_small")
+    check_inputs(g, *c.values())
+    out = so.upsample_flow(c["flow"].numpy(), c["mask"].numpy())
+    # same op sequence; ATen's vectorised exp (Sleef) and its 9-term sums differ from libm / sequential
+    # order by a few ulp: 1.1e-5 on |v| up to 82
+    assert max_abs(out, g["out"]) <= 3e-5
+
+
 # ---------------------------------------------------------------- W3k
 def test_tps_kornia():
     """warp_image_tps of the reference's kornia_tps.py (warp_points_tps / create_meshgrid restated

@@ -74,6 +74,8 @@ def main():
     report("composite_test_out", timeit(lambda: sb.composite_test_out(h1, h2, fw, occ)), px * 119)
     net_out = torch.rand(B, 1, S, S, device="cuda", generator=g)
     report("build_model", timeit(lambda: sb.build_model(lambda *a: net_out, img, img, img, img)), px * 88)
+    lo2, um = rnd(B, 2, 64, 64), rnd(B, 576, 64, 64)
+    report("upsample_flow (convex 8x)", timeit(lambda: sb.decoder.upsample_flow(lo2, um)), B * 4096 * (576 + 128 + 2) * 4)
     ys, xs = torch.meshgrid(torch.linspace(-1, 1, 13, device="cuda"), torch.linspace(-1, 1, 13, device="cuda"), indexing="ij")
     sp = torch.stack([xs, ys], -1).reshape(1, -1, 2).repeat(B, 1, 1)
     tg = sp + 0.02 * rnd(B, 169, 2)

@@ -204,6 +204,19 @@ int sb_tps_kornia_warp(const float* image, const float* centers, const float* kw
 int sb_grid_sample(const float* img, const float* grid, float* out, int N, int C, int H, int W,
                    int Ho, int Wo, int align_corners, sb_stream_t stream);
 
+/* ------------------------------------------------------------------ N1 ("next" row 1)
+ * GMA attention / aggregation (core/FlowFormer/PerCostFormer3/gma.py:54-76, :102-115).
+ *   sb_softmax_rows: in-place softmax over rows of a dense fp32 matrix (the `sim.softmax(dim=-1)`
+ *     of gma.py:73 applied to the q.k^T volume produced by sb_corr); to_tf32 != 0 rounds the
+ *     probabilities to TF32 (round-to-nearest) so sb_attn_aggregate's tensor-core read is unbiased.
+ *   sb_attn_aggregate: out[bh, n, i] = (residual[bh, n, i] +) gamma * sum_j attn[bh, i, j] * v[bh, n, j]
+ *     attn [BH, Nq, Nk], v [BH, d, Nk] (the 1x1-conv layout), out / residual [BH, d, Nq]; d = 128;
+ *     residual and gamma (DEVICE pointer to one float) are optional (NULL). */
+int sb_softmax_rows(float* x, long long rows, int n, long long row_stride, int to_tf32,
+                    sb_stream_t stream);
+int sb_attn_aggregate(const float* attn, const float* v, const float* residual, const float* gamma,
+                      float* out, int BH, int Nq, int Nk, int d, sb_stream_t stream);
+
 /* ------------------------------------------------------------------ N2 ("next" row 2)
  * Replaces MemoryDecoder.upsample_flow(flow, mask)
  * (core/FlowFormer/PerCostFormer3/decoder.py:214-225, called every GRU iteration at :331):

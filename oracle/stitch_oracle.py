@@ -197,6 +197,54 @@ def tps_transformer(U, source, target, out_size, return_indices=False, return_co
     return res[0] if len(res) == 1 else tuple(res)
 
 
+# ----------------------------------------------------------------- N1
+def gma_attention(fmap, to_qk_weight, heads=1, scale=None, bf16_inputs=False):
+    """Attention.forward (gma.py:54-76) in numpy: fp32 1x1 conv, fp64 contraction, softmax over keys.
+    bf16_inputs=True rounds scale*q and k to bf16 first (what the tensor-core kernel contracts)."""
+    import torch
+    fm = _f32(fmap)
+    wq = _f32(to_qk_weight).reshape(to_qk_weight.shape[0], -1)
+    b, c, h, w = fm.shape
+    qk = np.einsum("oc,bcn->bon", wq, fm.reshape(b, c, -1)).astype(np.float32)
+    inner = qk.shape[1] // 2
+    d = inner // heads
+    scale = d ** -0.5 if scale is None else scale
+    q = (np.float32(scale) * qk[:, :inner]).reshape(b * heads, d, -1)
+    k = qk[:, inner:].reshape(b * heads, d, -1)
+    n = h * w
+    return gma_attention_from_qk(q, k, bf16_inputs).reshape(b, heads, n, n)
+
+
+def gma_attention_from_qk(q, k, bf16_inputs=False):
+    """softmax over keys of q^T k for q, k [BH, d, ...]; fp64 contraction."""
+    import torch
+    q, k = _f32(q), _f32(k)
+    q = q.reshape(q.shape[0], q.shape[1], -1)
+    k = k.reshape(k.shape[0], k.shape[1], -1)
+    if bf16_inputs:
+        q = torch.from_numpy(q).bfloat16().float().numpy()
+        k = torch.from_numpy(k).bfloat16().float().numpy()
+    sim = np.matmul(q.transpose(0, 2, 1).astype(np.float64), k.astype(np.float64))
+    sim -= sim.max(axis=-1, keepdims=True)
+    e = np.exp(sim)
+    attn = e / e.sum(axis=-1, keepdims=True)
+    return attn.astype(np.float32)
+
+
+def gma_aggregate(attn, fmap, to_v_weight, gamma, heads=1):
+    """Aggregate.forward (gma.py:102-115), project == None: fmap + gamma * (attn @ v)."""
+    fm = _f32(fmap)
+    wv = _f32(to_v_weight).reshape(to_v_weight.shape[0], -1)
+    b, c, h, w = fm.shape
+    n = h * w
+    v = np.einsum("oc,bcn->bon", wv, fm.reshape(b, c, n)).astype(np.float32)
+    d = v.shape[1] // heads
+    a = _f32(attn).reshape(b * heads, n, n).astype(np.float64)
+    out = np.matmul(a, v.reshape(b * heads, d, n).transpose(0, 2, 1).astype(np.float64))   # [bh, i, d]
+    out = out.transpose(0, 2, 1).reshape(b, heads * d, h, w).astype(np.float32)
+    return (fm + np.float32(gamma) * out).astype(np.float32)
+
+
 # ----------------------------------------------------------------- N2
 def upsample_flow(flow, mask):
     """MemoryDecoder.upsample_flow (decoder.py:214-225)."""

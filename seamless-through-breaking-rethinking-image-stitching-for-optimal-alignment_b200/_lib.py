@@ -42,6 +42,8 @@ SIGNATURES = {
     "sb_tps_warp": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_tps_kornia_warp": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_grid_sample": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sb_softmax_rows": (c_int, [_P, c_longlong, c_int, c_longlong, c_int, _P]),
+    "sb_attn_aggregate": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_upsample_flow": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "sb_range_map": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_morph_open": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

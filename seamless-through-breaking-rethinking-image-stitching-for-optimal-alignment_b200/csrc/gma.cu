@@ -1,0 +1,307 @@
+// gma.cu — N1 ("next" row 1): GMA attention and aggregation.
+// Replaces the dense parts of
+//   Attention.forward  (core/FlowFormer/PerCostFormer3/gma.py:54-76):  attn = softmax(scale*q . k^T)
+//   Aggregate.forward  (gma.py:102-115):  out = fmap + gamma * (attn @ v)   (project == None)
+// called once (decoder.py:283) resp. every GRU iteration (gru.py:324 via GMAUpdateBlock).
+//
+//  * q.k^T is the same all-pairs contraction as the cost volume (K = dim_head = 128) and runs on
+//    corr_umma_kernel (corr_tcgen05.cu); softmax_rows_kernel below normalises the rows in place and
+//    rounds the probabilities to TF32 (round-to-nearest), so that
+//  * attn_v_umma_kernel can feed the fp32 attention matrix straight to the tensor cores as
+//    tcgen05.mma.kind::tf32 operands (no conversion pass, no bf16 copy): per (batch*head, 128-query
+//    block) tile, D[128 x 128] += A[128 x 32] . B[128 x 32]^T over K = Nk keys, A = attn rows
+//    (K-major, 128-byte rows = 32 fp32, SWIZZLE_128B), B = v [d, Nk] (K-major as the 1x1 conv leaves
+//    it).  6-stage TMA ring (32 KB per stage), one elected MMA thread, fp32 accumulators in TMEM
+//    (double-buffered), epilogue warps write D transposed ([d, Nq], the conv layout the reference
+//    rearranges to) fused with the residual fmap + gamma * out.
+//    Roofline: HBM — the attention matrix (Nq*Nk*4 B per batch*head) is read once per call; the
+//    reference reads it with an fp32 cuBLAS bmm (FFMA pipe).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "tmap.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------ softmax
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+template <bool IS_MAX>
+__device__ __forceinline__ float block_reduce(float v, float* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = IS_MAX ? fmaxf(v, t) : v + t;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  float r = s_red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) r = IS_MAX ? fmaxf(r, s_red[w]) : r + s_red[w];
+  __syncthreads();
+  return r;
+}
+
+// one CTA (256 threads) per row; the row lives in registers between the passes (n <= 256 * 4 * kMaxVec)
+constexpr int kSoftmaxVec = 8;   // float4 per thread -> rows up to 8192
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(float* __restrict__ x, long long rows, int n, long long row_stride, int to_tf32) {
+  __shared__ float s_red[8];
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    float* p = x + row * row_stride;
+    float4 v[kSoftmaxVec];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kSoftmaxVec; ++i) {
+      const int c = (i * 256 + threadIdx.x) * 4;
+      if (c < n) {
+        v[i] = *reinterpret_cast<const float4*>(p + c);
+        mx = fmaxf(fmaxf(fmaxf(mx, v[i].x), fmaxf(v[i].y, v[i].z)), v[i].w);
+      }
+    }
+    mx = block_reduce<true>(mx, s_red);
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kSoftmaxVec; ++i) {
+      const int c = (i * 256 + threadIdx.x) * 4;
+      if (c < n) {
+        v[i].x = expf(v[i].x - mx); v[i].y = expf(v[i].y - mx);
+        v[i].z = expf(v[i].z - mx); v[i].w = expf(v[i].w - mx);
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    sum = block_reduce<false>(sum, s_red);
+#pragma unroll
+    for (int i = 0; i < kSoftmaxVec; ++i) {
+      const int c = (i * 256 + threadIdx.x) * 4;
+      if (c < n) {
+        float4 o = make_float4(v[i].x / sum, v[i].y / sum, v[i].z / sum, v[i].w / sum);
+        if (to_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        *reinterpret_cast<float4*>(p + c) = o;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------- attn @ v
+constexpr int GM = 128, GN = 128, GK = 32;           // tile; K step = 32 fp32 = one 128-byte swizzle row
+constexpr int kGStages = 6;
+constexpr int kGStageBytes = (GM + GN) * 128;        // A 16 KB + B 16 KB
+constexpr int kGSmemTotal = kGStages * kGStageBytes + 256 + 1024;
+constexpr int kGAccBufs = 2;
+constexpr int kGTmemCols = 256;
+
+// instruction descriptor: D = f32, A = B = TF32 (format 2), both K-major, N = 128, M = 128
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) |
+                                ((uint32_t)(GM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct AttnVParams {
+  int BH, Nq, Nk, d;            // batch*heads, queries, keys, head dim (<= 128)
+  int MB, KS;                   // query blocks, K steps
+  long long n_tiles;
+  const float* residual;        // [BH, d, Nq] or nullptr
+  const float* gamma;           // device scalar or nullptr (1.0)
+  float* out;                   // [BH, d, Nq]
+  unsigned int* dbg;
+};
+
+__global__ void __launch_bounds__(256, 1)
+attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const AttnVParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sBar = smem_base + kGStages * kGStageBytes;
+  const uint32_t bar_full = sBar;                       // [kGStages]
+  const uint32_t bar_empty = sBar + 8 * kGStages;       // [kGStages]
+  const uint32_t bar_t_full = sBar + 16 * kGStages;     // [kGAccBufs]
+  const uint32_t bar_t_empty = bar_t_full + 8 * kGAccBufs;
+  const uint32_t tmem_slot = bar_t_empty + 8 * kGAccBufs;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kGStages * kGStageBytes + 16 * kGStages + 16 * kGAccBufs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kGStages; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < kGAccBufs; ++a) {
+      ptx::mbar_init(bar_t_full + 8 * a, 1);
+      ptx::mbar_init(bar_t_empty + 8 * a, 4);           // one elected lane per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, kGTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================================================ producer
+    if (lane == 0) {
+      uint32_t stage = 0, par = 0;
+      for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int mb = (int)(t % p.MB), bh = (int)(t / p.MB);
+        for (int ks = 0; ks < p.KS; ++ks) {
+          ptx::mbar_wait(bar_empty + 8 * stage, par ^ 1, 0x21, p.dbg);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kGStageBytes);
+          const uint32_t sa = smem_base + stage * kGStageBytes;
+          ptx::tma_load_3d(sa, &map_a, bar_full + 8 * stage, ks * GK, mb * GM, bh);
+          ptx::tma_load_3d(sa + GM * 128, &map_b, bar_full + 8 * stage, ks * GK, 0, bh);
+          if (++stage == kGStages) { stage = 0; par ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, par = 0, acc = 0, acc_par = 0;
+      for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        ptx::mbar_wait(bar_t_empty + 8 * acc, acc_par ^ 1, 0x22, p.dbg);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * GN;
+        for (int ks = 0; ks < p.KS; ++ks) {
+          ptx::mbar_wait(bar_full + 8 * stage, par, 0x23, p.dbg);
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = smem_base + stage * kGStageBytes;
+          const uint64_t adesc = ptx::umma_desc_k_sw128(sa);
+          const uint64_t bdesc = ptx::umma_desc_k_sw128(sa + GM * 128);
+#pragma unroll
+          for (int k = 0; k < GK / 8; ++k)   // 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
+            umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdescTf32, (ks | k) != 0);
+          ptx::umma_commit(bar_empty + 8 * stage);      // stage reusable once these MMAs retire
+          if (++stage == kGStages) { stage = 0; par ^= 1; }
+        }
+        ptx::umma_commit(bar_t_full + 8 * acc);         // accumulator ready for the epilogue
+        if (++acc == kGAccBufs) { acc = 0; acc_par ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================================================ epilogue
+    const int wq = warp - 4;                            // TMEM lane quarter == warp % 4
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const float g = p.gamma ? __ldg(p.gamma) : 1.0f;
+    uint32_t acc = 0, acc_par = 0;
+    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      const int mb = (int)(t % p.MB), bh = (int)(t / p.MB);
+      const int i = mb * GM + wq * 32 + lane;           // query index
+      const bool ok = i < p.Nq;
+      ptx::mbar_wait(bar_t_full + 8 * acc, acc_par, 0x24, p.dbg);
+      ptx::tc_fence_after_sync();
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(lane_taddr + acc * GN + sl * 32, r);
+        ptx::tmem_ld_wait();
+        // D[i, n] -> out[bh, n, i]: for every n the warp writes 32 consecutive queries (128 bytes)
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int n = sl * 32 + c;
+          if (ok && n < p.d) {
+            const size_t o = ((size_t)bh * p.d + n) * p.Nq + i;
+            const float a = __uint_as_float(r[c]);
+            // out = fmap + gamma * out  (gma.py:113): one rounding per op like the reference
+            const float val = p.residual ? fadd(__ldg(p.residual + o), fmul(g, a)) : (p.gamma ? fmul(g, a) : a);
+            stg_stream(p.out + o, val);
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_t_empty + 8 * acc);
+      if (++acc == kGAccBufs) { acc = 0; acc_par ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kGTmemCols);
+  }
+}
+
+}  // namespace sb
+
+extern "C" int sb_softmax_rows(float* x, long long rows, int n, long long row_stride, int to_tf32,
+                               sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(rows >= 0 && n >= 0 && row_stride >= n, SB_EINVAL, "sb_softmax_rows: bad size");
+  if (rows == 0 || n == 0) return SB_OK;
+  SB_REQUIRE(x != nullptr, SB_EINVAL, "sb_softmax_rows: null pointer");
+  SB_REQUIRE((n & 3) == 0 && (row_stride & 3) == 0 && aligned16(x), SB_EUNSUP,
+             "sb_softmax_rows: n and row_stride must be multiples of 4 floats, x 16-byte aligned");
+  SB_REQUIRE(n <= 256 * 4 * kSoftmaxVec, SB_EUNSUP, "sb_softmax_rows: rows longer than %d", 256 * 4 * kSoftmaxVec);
+  long long blocks = rows < (long long)kNumSMs * 8 ? rows : (long long)kNumSMs * 8;
+  softmax_rows_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, rows, n, row_stride, to_tf32);
+  SB_LAUNCH_CHECK("softmax_rows_kernel");
+  return SB_OK;
+}
+
+extern "C" int sb_attn_aggregate(const float* attn, const float* v, const float* residual,
+                                 const float* gamma, float* out, int BH, int Nq, int Nk, int d,
+                                 sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(BH >= 0 && Nq >= 0 && Nk >= 0 && d >= 0, SB_EINVAL, "sb_attn_aggregate: bad size");
+  if (BH == 0 || Nq == 0 || d == 0) return SB_OK;
+  SB_REQUIRE(attn && v && out, SB_EINVAL, "sb_attn_aggregate: null pointer");
+  SB_REQUIRE(Nk > 0, SB_EINVAL, "sb_attn_aggregate: no keys");
+  SB_REQUIRE(d == GN, SB_EUNSUP, "sb_attn_aggregate: dim_head must be %d (got %d)", GN, d);
+  SB_REQUIRE((Nk & 3) == 0 && aligned16(attn) && aligned16(v), SB_EUNSUP,
+             "sb_attn_aggregate: Nk must be a multiple of 4 and attn / v 16-byte aligned (TMA strides)");
+  CUtensorMap map_a, map_b;
+  int rc = make_map_3d_ex(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, attn, (unsigned long long)Nk,
+                          (unsigned long long)Nq, (unsigned long long)BH, GK, GM, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "attn");
+  if (rc) return rc;
+  rc = make_map_3d_ex(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v, (unsigned long long)Nk,
+                      (unsigned long long)d, (unsigned long long)BH, GK, GN, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "v");
+  if (rc) return rc;
+  AttnVParams p;
+  p.BH = BH; p.Nq = Nq; p.Nk = Nk; p.d = d;
+  p.MB = (Nq + GM - 1) / GM;
+  p.KS = (Nk + GK - 1) / GK;
+  p.n_tiles = (long long)BH * p.MB;
+  p.residual = residual; p.gamma = gamma; p.out = out;
+  p.dbg = debug_word_device();
+  if (!p.dbg) return SB_ECUDA;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    attr_set = true;
+  }
+  const int grid = (int)(p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs);
+  attn_v_umma_kernel<<<grid, 256, kGSmemTotal, as_stream(stream)>>>(map_a, map_b, p);
+  SB_LAUNCH_CHECK("attn_v_umma_kernel");
+  return SB_OK;
+}

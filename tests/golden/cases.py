@@ -149,6 +149,17 @@ def tps_small():
     return dict(U=base[None].repeat(b, 1, 1, 1).contiguous(), source=src, target=tgt, out_size=(32, 40))
 
 
+# ------------------------------------------------------------------ N1
+def gma_small():
+    """Attention / Aggregate as decoder.py:197 / gru.py:316 build them: dim = 128, heads = 1, dim_head = 128."""
+    g = _g(70)
+    fmap = torch.randn(2, 128, 12, 16, generator=g)
+    motion = torch.randn(2, 128, 12, 16, generator=g)
+    w_qk = (torch.rand(256, 128, 1, 1, generator=g) * 2 - 1) * (3.0 / 128 ** 0.5)   # sharper than the default init
+    w_v = (torch.rand(128, 128, 1, 1, generator=g) * 2 - 1) * (1.0 / 128 ** 0.5)
+    return dict(fmap=fmap, motion=motion, w_qk=w_qk, w_v=w_v, gamma=torch.tensor([0.7]))
+
+
 # ------------------------------------------------------------------ N2
 def upsample_small():
     g = _g(60)

@@ -193,6 +193,15 @@ def main():
     r = ref_build_model(lambda *a: c["net_out"], c["warp1"], c["warp2"], c["mask1"], c["mask2"])
     save("build_model", cases.checksum(*c.values()), **{k: v.numpy() for k, v in r.items()})
 
+    # ---------------------------------------------------------------- N1
+    import core.FlowFormer.PerCostFormer3.gma as ref_gma
+    c = cases.gma_small()
+    att = ref_gma.Attention(args=None, dim=128, heads=1, max_pos_size=160, dim_head=128)
+    agg = ref_gma.Aggregate(args=None, dim=128, dim_head=128, heads=1)
+    att.to_qk.weight.data.copy_(c["w_qk"]); agg.to_v.weight.data.copy_(c["w_v"]); agg.gamma.data.copy_(c["gamma"])
+    attn = att(c["fmap"])
+    save("gma_small", cases.checksum(*c.values()), attn=attn.numpy(), out=agg(attn, c["motion"]).numpy())
+
     # ---------------------------------------------------------------- N2
     c = cases.upsample_small()
     save("upsample_small", cases.checksum(*c.values()), out=MemoryDecoder.upsample_flow(None, c["flow"], c["mask"]).numpy())

@@ -323,6 +323,66 @@ def test_tps_169_points_vs_oracle(sb):
     assert max_abs(np.where(ok, host(out), 0), np.where(ok, ref, 0)) <= 1e-3
 
 
+# ===================================================================== N1 (next row 1)
+def test_gma_golden(sb):
+    c = cases.gma_small()
+    g = golden("gma_small")
+    check_inputs(g, *c.values())
+    attn = sb.gma.attention(cu(c["fmap"]), cu(c["w_qk"]), heads=1)
+    a = host(attn)
+    assert a.shape == g["attn"].shape
+    # kernel check: the same contraction on the bf16-rounded projections torch produced on this GPU
+    # (fp64), + TF32 rounding of the probabilities (2^-11)
+    q, k = sb.gma.project_qk(cu(c["fmap"]), cu(c["w_qk"]), heads=1)
+    a_bf = so.gma_attention_from_qk(host(q), host(k), bf16_inputs=True).reshape(a.shape)
+    assert max_abs(a, a_bf) <= 6e-4
+    assert abs(float(a.sum(-1).mean()) - 1.0) <= 1e-3
+    # contract vs the fp32 reference: < 2 % of the row maximum
+    assert (np.abs(a - g["attn"]).max(-1) / g["attn"].max(-1)).max() <= 2e-2
+    out = host(sb.gma.aggregate(attn, cu(c["motion"]), cu(c["w_v"]), cu(c["gamma"])))
+    scale = float(np.abs(g["out"]).max())
+    # kernel check: fp64 aggregate of the kernel's own attention (TF32 operands: 2^-11 relative)
+    assert max_abs(out, so.gma_aggregate(a, c["motion"].numpy(), c["w_v"].numpy(), float(c["gamma"]))) <= 2e-3 * scale
+    assert max_abs(out, g["out"]) <= 1e-2 * scale
+    # module mirrors with the reference's constructor arguments (decoder.py:197, gru.py:316)
+    att_m = sb.gma.Attention(args=None, dim=128, heads=1, max_pos_size=160, dim_head=128).cuda()
+    agg_m = sb.gma.Aggregate(args=None, dim=128, dim_head=128, heads=1).cuda()
+    att_m.to_qk.weight.data.copy_(c["w_qk"]); agg_m.to_v.weight.data.copy_(c["w_v"]); agg_m.gamma.data.copy_(c["gamma"])
+    with torch.no_grad():
+        o2 = host(agg_m(att_m(cu(c["fmap"])), cu(c["motion"])))
+    assert max_abs(o2, out) == 0.0
+
+
+def test_gma_full_size_vs_torch(sb):
+    """512^2 shape (N = 4096 tokens), batch 2: attn @ v against torch fp32 on the same attention."""
+    gen = torch.Generator(device="cuda").manual_seed(71)
+    fmap = torch.randn(2, 128, 64, 64, device="cuda", generator=gen)
+    w_qk = (torch.rand(256, 128, 1, 1, device="cuda", generator=gen) * 2 - 1) * 0.25
+    w_v = (torch.rand(128, 128, 1, 1, device="cuda", generator=gen) * 2 - 1) * 0.09
+    gamma = torch.tensor([0.5], device="cuda")
+    attn = sb.gma.attention(fmap, w_qk)
+    assert tuple(attn.shape) == (2, 1, 4096, 4096)
+    rs = attn.sum(-1)
+    assert float((rs - 1).abs().max()) <= 2e-3
+    out = sb.gma.aggregate(attn, fmap, w_v, gamma)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        v = torch.nn.functional.conv2d(fmap, w_v).view(2, 128, 4096)
+        ref = fmap + gamma * torch.einsum("bij,bdj->bdi", attn.view(2, 4096, 4096).double(), v.double()).float().view(2, 128, 64, 64)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    err = float((out - ref).abs().max())
+    assert err <= 2e-3 * float(ref.abs().max()), err
+    # ragged token count (N = 30 x 46 = 1380: not a multiple of the 128-query tile or the 32-key step)
+    fm2 = torch.randn(1, 128, 30, 46, device="cuda", generator=gen)
+    a2 = sb.gma.attention(fm2, w_qk)
+    o2 = sb.gma.aggregate(a2, fm2, w_v, gamma)
+    v2 = torch.nn.functional.conv2d(fm2, w_v).view(1, 128, 1380)
+    r2 = fm2 + gamma * torch.einsum("bij,bdj->bdi", a2.view(1, 1380, 1380).double(), v2.double()).float().view(1, 128, 30, 46)
+    assert float((o2 - r2).abs().max()) <= 2e-3 * float(r2.abs().max())
+
+
 # ===================================================================== N2 (next row 2)
 def test_upsample_flow_golden(sb):
     c = cases.upsample_small()

@@ -126,6 +126,20 @@ def test_tps():
     assert max_abs(np.where(ok, out, 0), np.where(ok, g["out"], 0)) <= 1e-3
 
 
+# ---------------------------------------------------------------- N1
+def test_gma_attention_and_aggregate():
+    c = cases.gma_small()
+    g = golden("gma_small")
+    check_inputs(g, *c.values())
+    attn = so.gma_attention(c["fmap"].numpy(), c["w_qk"].numpy())
+    assert max_abs(attn, g["attn"]) <= 5e-6
+    out = so.gma_aggregate(g["attn"], c["motion"].numpy(), c["w_v"].numpy(), float(c["gamma"]))
+    assert max_abs(out, g["out"]) <= 5e-6
+    # the tensor-core contract: bf16-rounded q, k move the probabilities by < 2 % of the row maximum
+    attn_bf = so.gma_attention(c["fmap"].numpy(), c["w_qk"].numpy(), bf16_inputs=True)
+    assert (np.abs(attn_bf - g["attn"]).max(-1) / g["attn"].max(-1)).max() <= 2e-2
+
+
 # ---------------------------------------------------------------- N2
 def test_upsample_flow():
     c = cases.upsample_small()

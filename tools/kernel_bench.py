@@ -74,6 +74,21 @@ def main():
     report("composite_test_out", timeit(lambda: sb.composite_test_out(h1, h2, fw, occ)), px * 119)
     net_out = torch.rand(B, 1, S, S, device="cuda", generator=g)
     report("build_model", timeit(lambda: sb.build_model(lambda *a: net_out, img, img, img, img)), px * 88)
+    # ---- GMA (next row 1): attention once, aggregate per GRU iteration
+    fm = rnd(B, 128, 64, 64)
+    w_qk, w_v, gam = rnd(256, 128, 1, 1) * 0.02, rnd(128, 128, 1, 1) * 0.09, torch.tensor([0.5], device="cuda")
+    attn = sb.gma.attention(fm, w_qk)
+    sim = torch.empty_like(attn)
+    report("gma softmax_rows (in place)", timeit(lambda: sb.gma.softmax_rows_(sim.copy_(attn)) and None, n=5) - timeit(lambda: sim.copy_(attn) and None, n=5), B * n * n * 8)
+    vv = torch.nn.functional.conv2d(fm, w_v).view(B, 128, n)
+    ms = timeit(lambda: sb.gma.attn_matmul_v(attn.view(B, n, n), vv, residual=fm.view(B, 128, n), gamma=gam), n=10)
+    report("gma attn @ v (tf32 tcgen05)", ms, B * (n * n * 4 + 3 * n * 128 * 4))
+    print(f"{'':34s} tensor: {B*2*n*n*128/ms/1e9:.0f} TFLOP/s (tf32)")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    report("  torch fp32 bmm (reference path)", timeit(lambda: torch.bmm(attn.view(B, n, n), vv.transpose(1, 2)), n=3), B * (n * n * 4 + 2 * n * 128 * 4))
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    del attn, sim
     lo2, um = rnd(B, 2, 64, 64), rnd(B, 576, 64, 64)
     report("upsample_flow (convex 8x)", timeit(lambda: sb.decoder.upsample_flow(lo2, um)), B * 4096 * (576 + 128 + 2) * 4)
     ys, xs = torch.meshgrid(torch.linspace(-1, 1, 13, device="cuda"), torch.linspace(-1, 1, 13, device="cuda"), indexing="ij")

@@ -90,12 +90,11 @@ softmax_rows_kernel(float* __restrict__ x, long long rows, int n, long long row_
 }
 
 // ------------------------------------------------------------- attn @ v
-constexpr int GM = 128, GN = 128, GK = 32;           // tile; K step = 32 fp32 = one 128-byte swizzle row
-constexpr int kGStages = 6;
-constexpr int kGStageBytes = (GM + GN) * 128;        // A 16 KB + B 16 KB
-constexpr int kGSmemTotal = kGStages * kGStageBytes + 256 + 1024;
-constexpr int kGAccBufs = 2;
-constexpr int kGTmemCols = 256;
+constexpr int GM = 128, GN = 128, GK = 32;           // block; K step = 32 fp32 = one 128-byte swizzle row
+constexpr int kGBlkBytes = GM * 128;                 // one operand block of one K step: 128 rows x 128 B = 16 KB
+constexpr int kGRingBudget = 192 * 1024;
+constexpr int kGSmemTotal = kGRingBudget + 256 + 1024;
+constexpr int kGTmemCols = 512;
 
 // instruction descriptor: D = f32, A = B = TF32 (format 2), both K-major, N = 128, M = 128
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) |
@@ -112,29 +111,35 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 
 struct AttnVParams {
-  int BH, Nq, Nk, d;            // batch*heads, queries, keys, head dim (<= 128)
-  int MB, KS;                   // query blocks, K steps
-  long long n_tiles;
+  int BH, Nq, Nk, d;            // batch*heads, queries, keys, head dim (== 128)
+  int MU, KS;                   // units (MBLK query blocks each) per batch*head, K steps
+  long long n_units;
   const float* residual;        // [BH, d, Nq] or nullptr
   const float* gamma;           // device scalar or nullptr (1.0)
   float* out;                   // [BH, d, Nq]
   unsigned int* dbg;
 };
 
+// MBLK = 128-query blocks per CTA unit: MBLK blocks share each v stage (A: MBLK x 16 KB + B: 16 KB
+// per K step, so v is re-read from L2 MBLK times less often), accumulators = MBLK x 128 TMEM columns,
+// 512 / (MBLK * 128) accumulator sets (MBLK = 4: one set, the epilogue is not overlapped).
+template <int MBLK>
 __global__ void __launch_bounds__(256, 1)
 attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const AttnVParams p) {
+  constexpr int kStageBytes = (MBLK + 1) * kGBlkBytes;
+  constexpr int kStages = kGRingBudget / kStageBytes;          // 6, 4, 2 for MBLK = 1, 2, 4
+  constexpr int kAccSets = 4 / MBLK;                           // 4, 2, 1
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sBar = smem_base + kGStages * kGStageBytes;
-  const uint32_t bar_full = sBar;                       // [kGStages]
-  const uint32_t bar_empty = sBar + 8 * kGStages;       // [kGStages]
-  const uint32_t bar_t_full = sBar + 16 * kGStages;     // [kGAccBufs]
-  const uint32_t bar_t_empty = bar_t_full + 8 * kGAccBufs;
-  const uint32_t tmem_slot = bar_t_empty + 8 * kGAccBufs;
+  const uint32_t sBar = smem_base + kGRingBudget;
+  const uint32_t bar_full = sBar;                       // [kStages]   (<= 6)
+  const uint32_t bar_empty = sBar + 48;                 // [kStages]
+  const uint32_t bar_t_full = sBar + 96;                // [kAccSets]  (<= 4)
+  const uint32_t bar_t_empty = sBar + 128;              // [kAccSets]
+  const uint32_t tmem_slot = sBar + 160;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kGStages * kGStageBytes + 16 * kGStages + 16 * kGAccBufs);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kGRingBudget + 160);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -142,11 +147,11 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     ptx::prefetch_tensormap(&map_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kGStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(bar_full + 8 * s, 1);
       ptx::mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int a = 0; a < kGAccBufs; ++a) {
+    for (int a = 0; a < kAccSets; ++a) {
       ptx::mbar_init(bar_t_full + 8 * a, 1);
       ptx::mbar_init(bar_t_empty + 8 * a, 4);           // one elected lane per epilogue warp
     }
@@ -165,15 +170,17 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // ================================================================ producer
     if (lane == 0) {
       uint32_t stage = 0, par = 0;
-      for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const int mb = (int)(t % p.MB), bh = (int)(t / p.MB);
+      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int mu = (int)(u % p.MU), bh = (int)(u / p.MU);
         for (int ks = 0; ks < p.KS; ++ks) {
           ptx::mbar_wait(bar_empty + 8 * stage, par ^ 1, 0x21, p.dbg);
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kGStageBytes);
-          const uint32_t sa = smem_base + stage * kGStageBytes;
-          ptx::tma_load_3d(sa, &map_a, bar_full + 8 * stage, ks * GK, mb * GM, bh);
-          ptx::tma_load_3d(sa + GM * 128, &map_b, bar_full + 8 * stage, ks * GK, 0, bh);
-          if (++stage == kGStages) { stage = 0; par ^= 1; }
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);   // rows past Nq / keys past Nk arrive as zeros
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          ptx::tma_load_3d(sa + MBLK * kGBlkBytes, &map_b, bar_full + 8 * stage, ks * GK, 0, bh);
+#pragma unroll
+          for (int m = 0; m < MBLK; ++m)
+            ptx::tma_load_3d(sa + m * kGBlkBytes, &map_a, bar_full + 8 * stage, ks * GK, (mu * MBLK + m) * GM, bh);
+          if (++stage == kStages) { stage = 0; par ^= 1; }
         }
       }
     }
@@ -182,24 +189,27 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // ============================================================== MMA issuer
     if (lane == 0) {
       uint32_t stage = 0, par = 0, acc = 0, acc_par = 0;
-      for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         ptx::mbar_wait(bar_t_empty + 8 * acc, acc_par ^ 1, 0x22, p.dbg);
         ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * GN;
+        const uint32_t d_tmem = tmem_base + acc * (MBLK * GN);
         for (int ks = 0; ks < p.KS; ++ks) {
           ptx::mbar_wait(bar_full + 8 * stage, par, 0x23, p.dbg);
           ptx::tc_fence_after_sync();
-          const uint32_t sa = smem_base + stage * kGStageBytes;
-          const uint64_t adesc = ptx::umma_desc_k_sw128(sa);
-          const uint64_t bdesc = ptx::umma_desc_k_sw128(sa + GM * 128);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint64_t bdesc = ptx::umma_desc_k_sw128(sa + MBLK * kGBlkBytes);
 #pragma unroll
-          for (int k = 0; k < GK / 8; ++k)   // 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
-            umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdescTf32, (ks | k) != 0);
+          for (int m = 0; m < MBLK; ++m) {
+            const uint64_t adesc = ptx::umma_desc_k_sw128(sa + m * kGBlkBytes);
+#pragma unroll
+            for (int k = 0; k < GK / 8; ++k)   // 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
+              umma_tf32(d_tmem + m * GN, adesc + 2 * k, bdesc + 2 * k, kIdescTf32, (ks | k) != 0);
+          }
           ptx::umma_commit(bar_empty + 8 * stage);      // stage reusable once these MMAs retire
-          if (++stage == kGStages) { stage = 0; par ^= 1; }
+          if (++stage == kStages) { stage = 0; par ^= 1; }
         }
-        ptx::umma_commit(bar_t_full + 8 * acc);         // accumulator ready for the epilogue
-        if (++acc == kGAccBufs) { acc = 0; acc_par ^= 1; }
+        ptx::umma_commit(bar_t_full + 8 * acc);         // accumulators ready for the epilogue
+        if (++acc == kAccSets) { acc = 0; acc_par ^= 1; }
       }
     }
     __syncwarp();
@@ -209,34 +219,37 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
     const float g = p.gamma ? __ldg(p.gamma) : 1.0f;
     uint32_t acc = 0, acc_par = 0;
-    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-      const int mb = (int)(t % p.MB), bh = (int)(t / p.MB);
-      const int i = mb * GM + wq * 32 + lane;           // query index
-      const bool ok = i < p.Nq;
+    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int mu = (int)(u % p.MU), bh = (int)(u / p.MU);
       ptx::mbar_wait(bar_t_full + 8 * acc, acc_par, 0x24, p.dbg);
       ptx::tc_fence_after_sync();
+#pragma unroll 1
+      for (int m = 0; m < MBLK; ++m) {
+        const int i = (mu * MBLK + m) * GM + wq * 32 + lane;   // query index
+        const bool ok = i < p.Nq;
+#pragma unroll 1
+        for (int sl = 0; sl < 4; ++sl) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_taddr + acc * (MBLK * GN) + m * GN + sl * 32, r);
+          ptx::tmem_ld_wait();
+          // D[i, n] -> out[bh, n, i]: for every n the warp writes 32 consecutive queries (128 bytes)
 #pragma unroll
-      for (int sl = 0; sl < 4; ++sl) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(lane_taddr + acc * GN + sl * 32, r);
-        ptx::tmem_ld_wait();
-        // D[i, n] -> out[bh, n, i]: for every n the warp writes 32 consecutive queries (128 bytes)
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int n = sl * 32 + c;
-          if (ok && n < p.d) {
-            const size_t o = ((size_t)bh * p.d + n) * p.Nq + i;
-            const float a = __uint_as_float(r[c]);
-            // out = fmap + gamma * out  (gma.py:113): one rounding per op like the reference
-            const float val = p.residual ? fadd(__ldg(p.residual + o), fmul(g, a)) : (p.gamma ? fmul(g, a) : a);
-            stg_stream(p.out + o, val);
+          for (int c = 0; c < 32; ++c) {
+            const int n = sl * 32 + c;
+            if (ok) {
+              const size_t o = ((size_t)bh * p.d + n) * p.Nq + i;
+              const float a = __uint_as_float(r[c]);
+              // out = fmap + gamma * out  (gma.py:113): one rounding per op like the reference
+              const float val = p.residual ? fadd(__ldg(p.residual + o), fmul(g, a)) : (p.gamma ? fmul(g, a) : a);
+              stg_stream(p.out + o, val);
+            }
           }
         }
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_t_empty + 8 * acc);
-      if (++acc == kGAccBufs) { acc = 0; acc_par ^= 1; }
+      if (++acc == kAccSets) { acc = 0; acc_par ^= 1; }
     }
   }
 
@@ -287,21 +300,31 @@ extern "C" int sb_attn_aggregate(const float* attn, const float* v, const float*
                       (unsigned long long)d, (unsigned long long)BH, GK, GN, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "v");
   if (rc) return rc;
+  const int MB = (Nq + GM - 1) / GM;
+  // query blocks per CTA: 2 share every v stage when that still leaves a unit per SM (measured at
+  // B=16, N=4096: MBLK 1 / 2 / 4 = 217 / 215 / 237 us — 4 has a single accumulator set, so its
+  // epilogue is exposed)
+  int mblk = tune_get(SB_TUNE_AGG_MBLK, 0);
+  if (mblk != 1 && mblk != 2 && mblk != 4) mblk = ((long long)BH * ((MB + 1) / 2) >= kNumSMs) ? 2 : 1;
   AttnVParams p;
   p.BH = BH; p.Nq = Nq; p.Nk = Nk; p.d = d;
-  p.MB = (Nq + GM - 1) / GM;
+  p.MU = (MB + mblk - 1) / mblk;
   p.KS = (Nk + GK - 1) / GK;
-  p.n_tiles = (long long)BH * p.MB;
+  p.n_units = (long long)BH * p.MU;
   p.residual = residual; p.gamma = gamma; p.out = out;
   p.dbg = debug_word_device();
   if (!p.dbg) return SB_ECUDA;
   static bool attr_set = false;
   if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
     attr_set = true;
   }
-  const int grid = (int)(p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs);
-  attn_v_umma_kernel<<<grid, 256, kGSmemTotal, as_stream(stream)>>>(map_a, map_b, p);
+  const int grid = (int)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
+  if (mblk == 4) attn_v_umma_kernel<4><<<grid, 256, kGSmemTotal, as_stream(stream)>>>(map_a, map_b, p);
+  else if (mblk == 2) attn_v_umma_kernel<2><<<grid, 256, kGSmemTotal, as_stream(stream)>>>(map_a, map_b, p);
+  else attn_v_umma_kernel<1><<<grid, 256, kGSmemTotal, as_stream(stream)>>>(map_a, map_b, p);
   SB_LAUNCH_CHECK("attn_v_umma_kernel");
   return SB_OK;
 }

@@ -20,7 +20,7 @@ from torch import nn
 from . import _lib
 from . import corr as corr_mod
 
-__all__ = ["attention", "aggregate", "project_qk", "Attention", "Aggregate", "softmax_rows_", "attn_matmul_v"]
+__all__ = ["attention", "aggregate", "project_qk", "attention_forward", "aggregate_forward", "Attention", "Aggregate", "softmax_rows_", "attn_matmul_v"]
 
 
 def softmax_rows_(x: torch.Tensor, to_tf32: bool = True) -> torch.Tensor:
@@ -92,6 +92,17 @@ def aggregate(attn, fmap, to_v_weight, gamma, project_weight=None, heads: int = 
     if project_weight is not None:
         out = F.conv2d(out, project_weight)
     return fm + gamma * out
+
+
+def attention_forward(self, fmap):
+    """Drop-in body for the reference's ``Attention.forward(self, fmap)`` (uses its ``to_qk``, ``heads``, ``scale``)."""
+    return attention(fmap, self.to_qk.weight, self.heads, self.scale)
+
+
+def aggregate_forward(self, attn, fmap):
+    """Drop-in body for the reference's ``Aggregate.forward(self, attn, fmap)``."""
+    return aggregate(attn, fmap, self.to_v.weight, self.gamma,
+                     None if self.project is None else self.project.weight, self.heads)
 
 
 class Attention(nn.Module):

@@ -10,7 +10,7 @@ __all__ = ["patch_reference"]
 
 
 def patch_reference(verbose: bool = False):
-    from . import composition, corr, decoder, kornia_tps, lookup, torch_homo_transform, torch_tps_transform, warp_utils
+    from . import composition, corr, decoder, gma, kornia_tps, lookup, torch_homo_transform, torch_tps_transform, warp_utils
 
     done = []
 
@@ -41,6 +41,8 @@ def patch_reference(verbose: bool = False):
          lookup.memory_decoder_encode_flow_token, cls="MemoryDecoder")
     _set("core.FlowFormer.PerCostFormer3.decoder", "upsample_flow",
          decoder.memory_decoder_upsample_flow, cls="MemoryDecoder")
+    _set("core.FlowFormer.PerCostFormer3.gma", "forward", gma.attention_forward, cls="Attention")
+    _set("core.FlowFormer.PerCostFormer3.gma", "forward", gma.aggregate_forward, cls="Aggregate")
     # tps_method="kornia" branch (tps_pipline.py:364-381 imports these two names at call time)
     _set("core.inference.tps_methods.kornia_tps", "warp_image_tps", kornia_tps.warp_image_tps)
     _set("core.inference.tps_methods.kornia_tps", "get_tps_transform", kornia_tps.get_tps_transform)

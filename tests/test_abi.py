@@ -96,7 +96,11 @@ def test_patch_reference_assigns_call_sites():
         assert th.transformer is stitch_b200.torch_homo_transform.transformer
         assert MemoryEncoder.corr is stitch_b200.corr.memory_encoder_corr
         assert MemoryDecoder.encode_flow_token is stitch_b200.lookup.memory_decoder_encode_flow_token
-        assert len(done) >= 12
+        assert MemoryDecoder.upsample_flow is stitch_b200.decoder.memory_decoder_upsample_flow
+        import core.FlowFormer.PerCostFormer3.gma as ref_gma
+        assert ref_gma.Attention.forward is stitch_b200.gma.attention_forward
+        assert ref_gma.Aggregate.forward is stitch_b200.gma.aggregate_forward
+        assert len(done) >= 15
     finally:
         for k in list(sys.modules):
             if k not in saved and (k.startswith("core") or k.startswith("timm") or k.startswith("skimage")):

@@ -218,6 +218,20 @@ int sb_softmax_rows(float* x, long long rows, int n, long long row_stride, int t
 int sb_attn_aggregate(const float* attn, const float* v, const float* residual, const float* gamma,
                       float* out, int BH, int Nq, int Nk, int d, sb_stream_t stream);
 
+/* D[bh] = A[bh] . B[bh]^T on the TF32 tensor cores (the kernel behind sb_attn_aggregate, row-major
+ * output): A [BH, M, K], B [BH, N, K] fp32 K-major, D [BH, M, N] fp32; K % 4 == 0. */
+int sb_gemm_nt_tf32(const float* A, const float* B, float* D, int BH, int M, int N, int K,
+                    sb_stream_t stream);
+
+/* ------------------------------------------------------------------ N3 ("next" row 3)
+ * Replaces UDIS2Network.CCL(feature_1, feature_2)  (core/UDIS2/Homography/network.py:147-199):
+ * L2-normalise over channels, 3x3-patch all-pairs correlation, softmax(10 x) over the patches,
+ * expected displacement. feature_1/2 [B,C,H,W] -> flow [B,2,H,W] (channel 0 = w, 1 = h).
+ * workspace: caller-provided, 256-byte aligned, >= sb_ccl_workspace_bytes(). H*W <= 4096, C % 4 == 0. */
+size_t sb_ccl_workspace_bytes(int B, int C, int H, int W);
+int sb_ccl(const float* feature_1, const float* feature_2, float* flow, void* workspace,
+           size_t workspace_bytes, int B, int C, int H, int W, float softmax_scale, sb_stream_t stream);
+
 /* ------------------------------------------------------------------ N2 ("next" row 2)
  * Replaces MemoryDecoder.upsample_flow(flow, mask)
  * (core/FlowFormer/PerCostFormer3/decoder.py:214-225, called every GRU iteration at :331):

@@ -245,6 +245,35 @@ def gma_aggregate(attn, fmap, to_v_weight, gamma, heads=1):
     return (fm + np.float32(gamma) * out).astype(np.float32)
 
 
+# ----------------------------------------------------------------- N3
+def ccl(feature_1, feature_2, softmax_scale=10.0):
+    """UDIS2Network.CCL (core/UDIS2/Homography/network.py:147-199) in numpy/fp64:
+    match[q, p] = sum over c and the 3x3 offsets d of nf1[c, p+d] * nf2[c, q+d] (zero outside either
+    map) — the conv2d of :161 written as nine shifted diagonals of the plain correlation."""
+    f1, f2 = _f32(feature_1).astype(np.float64), _f32(feature_2).astype(np.float64)
+    b, c, h, w = f1.shape
+    n = h * w
+    nf1 = f1 / np.maximum(np.sqrt((f1 * f1).sum(1, keepdims=True)), 1e-12)
+    nf2 = f2 / np.maximum(np.sqrt((f2 * f2).sum(1, keepdims=True)), 1e-12)
+    out = np.empty((b, 2, h, w), np.float32)
+    ys, xs = np.divmod(np.arange(n), w)
+    for i in range(b):
+        c0 = nf1[i].reshape(c, n).T @ nf2[i].reshape(c, n)                    # [p, q]
+        c0p = np.zeros((h + 2, w + 2, h + 2, w + 2))
+        c0p[1:-1, 1:-1, 1:-1, 1:-1] = c0.reshape(h, w, h, w)
+        match = np.zeros((h, w, h, w))
+        for dy in (0, 1, 2):
+            for dx in (0, 1, 2):
+                match += c0p[dy:dy + h, dx:dx + w, dy:dy + h, dx:dx + w]
+        m = match.reshape(n, n) * softmax_scale                                   # [p, q]
+        m -= m.max(axis=1, keepdims=True)
+        e = np.exp(m)
+        prob = e / e.sum(axis=1, keepdims=True)
+        out[i, 1] = (prob * (ys[None, :] - ys[:, None])).sum(1).reshape(h, w)    # flow_h
+        out[i, 0] = (prob * (xs[None, :] - xs[:, None])).sum(1).reshape(h, w)    # flow_w
+    return out
+
+
 # ----------------------------------------------------------------- N2
 def upsample_flow(flow, mask):
     """MemoryDecoder.upsample_flow (decoder.py:214-225)."""

@@ -111,8 +111,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 
 struct AttnVParams {
-  int BH, Nq, Nk, d;            // batch*heads, queries, keys, head dim (== 128)
+  int BH, Nq, Nk, d;            // batch*heads, queries (M), keys (K), head dim (transposed mode: == 128)
   int MU, KS;                   // units (MBLK query blocks each) per batch*head, K steps
+  int NT, ncols;                // row-major mode (plain batched D = A . B^T): column tiles, total columns
+  int row_major;                // 0: out[bh, n, i] (+ residual, gamma)   1: out[bh, i, n]
   long long n_units;
   const float* residual;        // [BH, d, Nq] or nullptr
   const float* gamma;           // device scalar or nullptr (1.0)
@@ -171,12 +173,14 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (lane == 0) {
       uint32_t stage = 0, par = 0;
       for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const int mu = (int)(u % p.MU), bh = (int)(u / p.MU);
+        const int nt = (int)(u % p.NT);
+        const long long u2 = u / p.NT;
+        const int mu = (int)(u2 % p.MU), bh = (int)(u2 / p.MU);
         for (int ks = 0; ks < p.KS; ++ks) {
           ptx::mbar_wait(bar_empty + 8 * stage, par ^ 1, 0x21, p.dbg);
           ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);   // rows past Nq / keys past Nk arrive as zeros
           const uint32_t sa = smem_base + stage * kStageBytes;
-          ptx::tma_load_3d(sa + MBLK * kGBlkBytes, &map_b, bar_full + 8 * stage, ks * GK, 0, bh);
+          ptx::tma_load_3d(sa + MBLK * kGBlkBytes, &map_b, bar_full + 8 * stage, ks * GK, nt * GN, bh);
 #pragma unroll
           for (int m = 0; m < MBLK; ++m)
             ptx::tma_load_3d(sa + m * kGBlkBytes, &map_a, bar_full + 8 * stage, ks * GK, (mu * MBLK + m) * GM, bh);
@@ -220,7 +224,9 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const float g = p.gamma ? __ldg(p.gamma) : 1.0f;
     uint32_t acc = 0, acc_par = 0;
     for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int mu = (int)(u % p.MU), bh = (int)(u / p.MU);
+      const int nt = (int)(u % p.NT);
+      const long long u2 = u / p.NT;
+      const int mu = (int)(u2 % p.MU), bh = (int)(u2 / p.MU);
       ptx::mbar_wait(bar_t_full + 8 * acc, acc_par, 0x24, p.dbg);
       ptx::tc_fence_after_sync();
 #pragma unroll 1
@@ -232,6 +238,22 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(lane_taddr + acc * (MBLK * GN) + m * GN + sl * 32, r);
           ptx::tmem_ld_wait();
+          if (p.row_major) {
+            // D[i, n] -> out[bh, i, nt*128 + n]: every thread writes its row's 32 floats (one 128-byte line)
+            const int n0 = nt * GN + sl * 32;
+            if (ok && n0 < p.ncols) {
+              float* orow = p.out + ((size_t)bh * p.Nq + i) * p.ncols + n0;
+              if (n0 + 32 <= p.ncols && (p.ncols & 3) == 0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                  stg_stream4(orow + 4 * c, make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                                        __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3])));
+              } else {
+                for (int c = 0; c < 32 && n0 + c < p.ncols; ++c) orow[c] = __uint_as_float(r[c]);
+              }
+            }
+            continue;
+          }
           // D[i, n] -> out[bh, n, i]: for every n the warp writes 32 consecutive queries (128 bytes)
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
@@ -279,6 +301,57 @@ extern "C" int sb_softmax_rows(float* x, long long rows, int n, long long row_st
   return SB_OK;
 }
 
+namespace sb {
+static int launch_attn_v(const CUtensorMap& map_a, const CUtensorMap& map_b, AttnVParams& p, int mblk,
+                         cudaStream_t stream) {
+  p.dbg = debug_word_device();
+  if (!p.dbg) return SB_ECUDA;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    attr_set = true;
+  }
+  const int grid = (int)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
+  if (mblk == 4) attn_v_umma_kernel<4><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
+  else if (mblk == 2) attn_v_umma_kernel<2><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
+  else attn_v_umma_kernel<1><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
+  SB_LAUNCH_CHECK("attn_v_umma_kernel");
+  return SB_OK;
+}
+}  // namespace sb
+
+// D[bh] = A[bh] . B[bh]^T on the TF32 tensor cores: A [BH, M, K], B [BH, N, K] (both K-major, fp32),
+// D [BH, M, N] fp32 row-major. Used by the CCL correlation (ccl.cu).
+extern "C" int sb_gemm_nt_tf32(const float* A, const float* B, float* D, int BH, int M, int N, int K,
+                               sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(BH >= 0 && M >= 0 && N >= 0 && K > 0, SB_EINVAL, "sb_gemm_nt_tf32: bad size");
+  if (BH == 0 || M == 0 || N == 0) return SB_OK;
+  SB_REQUIRE(A && B && D, SB_EINVAL, "sb_gemm_nt_tf32: null pointer");
+  SB_REQUIRE((K & 3) == 0 && aligned16(A) && aligned16(B) && aligned16(D), SB_EUNSUP,
+             "sb_gemm_nt_tf32: K must be a multiple of 4 and A / B / D 16-byte aligned");
+  CUtensorMap map_a, map_b;
+  int rc = make_map_3d_ex(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, (unsigned long long)K,
+                          (unsigned long long)M, (unsigned long long)BH, GK, GM, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "A");
+  if (rc) return rc;
+  rc = make_map_3d_ex(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, B, (unsigned long long)K,
+                      (unsigned long long)N, (unsigned long long)BH, GK, GN, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "B");
+  if (rc) return rc;
+  AttnVParams p;
+  p.BH = BH; p.Nq = M; p.Nk = K; p.d = N;
+  p.MU = (M + GM - 1) / GM;
+  p.KS = (K + GK - 1) / GK;
+  p.NT = (N + GN - 1) / GN; p.ncols = N; p.row_major = 1;
+  p.n_units = (long long)BH * p.MU * p.NT;
+  p.residual = nullptr; p.gamma = nullptr; p.out = D;
+  return launch_attn_v(map_a, map_b, p, 1, as_stream(stream));
+}
+
 extern "C" int sb_attn_aggregate(const float* attn, const float* v, const float* residual,
                                  const float* gamma, float* out, int BH, int Nq, int Nk, int d,
                                  sb_stream_t stream) {
@@ -310,21 +383,8 @@ extern "C" int sb_attn_aggregate(const float* attn, const float* v, const float*
   p.BH = BH; p.Nq = Nq; p.Nk = Nk; p.d = d;
   p.MU = (MB + mblk - 1) / mblk;
   p.KS = (Nk + GK - 1) / GK;
+  p.NT = 1; p.ncols = d; p.row_major = 0;
   p.n_units = (long long)BH * p.MU;
   p.residual = residual; p.gamma = gamma; p.out = out;
-  p.dbg = debug_word_device();
-  if (!p.dbg) return SB_ECUDA;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
-    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
-    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
-    attr_set = true;
-  }
-  const int grid = (int)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
-  if (mblk == 4) attn_v_umma_kernel<4><<<grid, 256, kGSmemTotal, as_stream(stream)>>>(map_a, map_b, p);
-  else if (mblk == 2) attn_v_umma_kernel<2><<<grid, 256, kGSmemTotal, as_stream(stream)>>>(map_a, map_b, p);
-  else attn_v_umma_kernel<1><<<grid, 256, kGSmemTotal, as_stream(stream)>>>(map_a, map_b, p);
-  SB_LAUNCH_CHECK("attn_v_umma_kernel");
-  return SB_OK;
+  return launch_attn_v(map_a, map_b, p, mblk, as_stream(stream));
 }

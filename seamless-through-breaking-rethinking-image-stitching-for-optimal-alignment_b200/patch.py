@@ -10,7 +10,7 @@ __all__ = ["patch_reference"]
 
 
 def patch_reference(verbose: bool = False):
-    from . import composition, corr, decoder, gma, kornia_tps, lookup, torch_homo_transform, torch_tps_transform, warp_utils
+    from . import composition, corr, decoder, gma, kornia_tps, lookup, udis2_homography, torch_homo_transform, torch_tps_transform, warp_utils
 
     done = []
 
@@ -43,6 +43,7 @@ def patch_reference(verbose: bool = False):
          decoder.memory_decoder_upsample_flow, cls="MemoryDecoder")
     _set("core.FlowFormer.PerCostFormer3.gma", "forward", gma.attention_forward, cls="Attention")
     _set("core.FlowFormer.PerCostFormer3.gma", "forward", gma.aggregate_forward, cls="Aggregate")
+    _set("core.UDIS2.Homography.network", "CCL", udis2_homography.udis2_network_ccl, cls="UDIS2Network")
     # tps_method="kornia" branch (tps_pipline.py:364-381 imports these two names at call time)
     _set("core.inference.tps_methods.kornia_tps", "warp_image_tps", kornia_tps.warp_image_tps)
     _set("core.inference.tps_methods.kornia_tps", "get_tps_transform", kornia_tps.get_tps_transform)

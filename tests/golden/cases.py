@@ -160,6 +160,15 @@ def gma_small():
     return dict(fmap=fmap, motion=motion, w_qk=w_qk, w_v=w_v, gamma=torch.tensor([0.7]))
 
 
+# ------------------------------------------------------------------ N3
+def ccl_small():
+    """Post-ReLU-like (non-negative) features with a shifted copy so the match volume has structure."""
+    g = _g(80)
+    f1 = torch.relu(torch.randn(2, 64, 10, 12, generator=g))
+    f2 = torch.roll(f1, shifts=(1, -2), dims=(2, 3)) + 0.3 * torch.relu(torch.randn(2, 64, 10, 12, generator=g))
+    return dict(feature_1=f1, feature_2=f2)
+
+
 # ------------------------------------------------------------------ N2
 def upsample_small():
     g = _g(60)

@@ -202,6 +202,12 @@ def main():
     attn = att(c["fmap"])
     save("gma_small", cases.checksum(*c.values()), attn=attn.numpy(), out=agg(attn, c["motion"]).numpy())
 
+    # ---------------------------------------------------------------- N3
+    from core.UDIS2.Homography.network import UDIS2Network
+    stub = SimpleNamespace(extract_patches=lambda x, kernel=3, stride=1: UDIS2Network.extract_patches(None, x, kernel, stride))
+    c = cases.ccl_small()
+    save("ccl_small", cases.checksum(*c.values()), flow=UDIS2Network.CCL(stub, c["feature_1"], c["feature_2"]).numpy())
+
     # ---------------------------------------------------------------- N2
     c = cases.upsample_small()
     save("upsample_small", cases.checksum(*c.values()), out=MemoryDecoder.upsample_flow(None, c["flow"], c["mask"]).numpy())

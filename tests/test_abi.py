@@ -100,7 +100,9 @@ def test_patch_reference_assigns_call_sites():
         import core.FlowFormer.PerCostFormer3.gma as ref_gma
         assert ref_gma.Attention.forward is stitch_b200.gma.attention_forward
         assert ref_gma.Aggregate.forward is stitch_b200.gma.aggregate_forward
-        assert len(done) >= 15
+        from core.UDIS2.Homography.network import UDIS2Network
+        assert UDIS2Network.CCL is stitch_b200.udis2_homography.udis2_network_ccl
+        assert len(done) >= 16
     finally:
         for k in list(sys.modules):
             if k not in saved and (k.startswith("core") or k.startswith("timm") or k.startswith("skimage")):

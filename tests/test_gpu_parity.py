@@ -383,6 +383,39 @@ def test_gma_full_size_vs_torch(sb):
     assert float((o2 - r2).abs().max()) <= 2e-3 * float(r2.abs().max())
 
 
+# ===================================================================== N3 (next row 3)
+def test_gemm_nt_tf32_vs_fp64(sb):
+    gen = torch.Generator(device="cuda").manual_seed(81)
+    for bh, m, n, k in ((2, 256, 128, 64), (3, 200, 136, 100), (1, 1024, 1024, 1024)):
+        a = torch.randn(bh, m, k, device="cuda", generator=gen)
+        b = torch.randn(bh, n, k, device="cuda", generator=gen)
+        d = sb.udis2_homography.gemm_nt_tf32(a, b)
+        ref = torch.einsum("bmk,bnk->bmn", a.double(), b.double())
+        err = float((d.double() - ref).abs().max())
+        # TF32 operands (10-bit mantissa, truncated by the tensor core): ~2^-10 * sqrt(K) * |a||b|
+        assert err <= 8e-3 * (k ** 0.5), (bh, m, n, k, err)
+
+
+def test_ccl_golden_and_full_size(sb):
+    c = cases.ccl_small()
+    g = golden("ccl_small")
+    check_inputs(g, *c.values())
+    flow = host(sb.udis2_homography.CCL(cu(c["feature_1"]), cu(c["feature_2"])))
+    assert flow.shape == g["flow"].shape
+    # TF32 contraction (10-bit mantissa): with only 64 channels every normalised element is large
+    # (~1/8), which is the worst case for the x10 softmax; the network's 1024-channel shape is ~3e-4
+    assert max_abs(flow, g["flow"]) <= 1e-2
+    # the shape the network uses (network.py:125-130): [B, 1024, 32, 32]; also a soft softmax (scale 1),
+    # which is far more sensitive to the correlation values than the reference's scale 10
+    gen = torch.Generator().manual_seed(82)
+    f1 = torch.relu(torch.randn(2, 1024, 32, 32, generator=gen))
+    f2 = torch.roll(f1, shifts=(2, -3), dims=(2, 3)) + 0.5 * torch.relu(torch.randn(2, 1024, 32, 32, generator=gen))
+    for scale, tol in ((10.0, 2e-3), (1.0, 2e-3)):
+        got = host(sb.udis2_homography.CCL(cu(f1), cu(f2), softmax_scale=scale))
+        ref = so.ccl(f1.numpy(), f2.numpy(), softmax_scale=scale)
+        assert max_abs(got, ref) <= tol, (scale, max_abs(got, ref))
+
+
 # ===================================================================== N2 (next row 2)
 def test_upsample_flow_golden(sb):
     c = cases.upsample_small()

@@ -140,6 +140,16 @@ def test_gma_attention_and_aggregate():
     assert (np.abs(attn_bf - g["attn"]).max(-1) / g["attn"].max(-1)).max() <= 2e-2
 
 
+# ---------------------------------------------------------------- N3
+def test_ccl():
+    c = cases.ccl_small()
+    g = golden("ccl_small")
+    check_inputs(g, *c.values())
+    flow = so.ccl(c["feature_1"].numpy(), c["feature_2"].numpy())
+    # fp64 restatement (nine shifted diagonals of the plain correlation) vs the reference's fp32 conv2d
+    assert max_abs(flow, g["flow"]) <= 5e-5
+
+
 # ---------------------------------------------------------------- N2
 def test_upsample_flow():
     c = cases.upsample_small()

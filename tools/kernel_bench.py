@@ -92,6 +92,11 @@ def main():
     report("  torch fp32 bmm (reference path)", timeit(lambda: torch.bmm(attn.view(B, n, n), vv.transpose(1, 2)), n=3), B * (n * n * 4 + 2 * n * 128 * 4))
     torch.backends.cuda.matmul.allow_tf32 = prev
     del attn, sim
+    # ---- CCL (next row 3): [B, 1024, 32, 32] features
+    cf1, cf2 = torch.relu(rnd(B, 1024, 32, 32)), torch.relu(rnd(B, 1024, 32, 32))
+    ms = timeit(lambda: sb.udis2_homography.CCL(cf1, cf2), n=10)
+    report("CCL (norm + tf32 corr + softmax-flow)", ms, B * (2 * 1024 * 1024 * 4 * 3 + 1024 * 1024 * 4 * 2))
+    print(f"{'':34s} {B*2*1024*1024*1024/ms/1e9:.0f} TFLOP/s on the contraction actually computed; reference form = 9x the FLOPs")
     lo2, um = rnd(B, 2, 64, 64), rnd(B, 576, 64, 64)
     report("upsample_flow (convex 8x)", timeit(lambda: sb.decoder.upsample_flow(lo2, um)), B * 4096 * (576 + 128 + 2) * 4)
     ys, xs = torch.meshgrid(torch.linspace(-1, 1, 13, device="cuda"), torch.linspace(-1, 1, 13, device="cuda"), indexing="ij")

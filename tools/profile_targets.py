@@ -17,6 +17,10 @@ occ = (torch.rand(B, 1, S, S, device="cuda", generator=g) < 0.8).float()
 src = sb.torch_DLT.corner_points(S, S, B, "cuda")
 M = sb.torch_DLT.norm_matrix(S / 8, S / 8)
 coords = sb.lookup.coords_grid(B, 64, 64, device="cuda") + rnd(B, 2, 64, 64) * 2
+fm = rnd(B, 128, 64, 64)
+w_qk, w_v, gam = rnd(256, 128, 1, 1) * 0.02, rnd(128, 128, 1, 1) * 0.09, torch.tensor([0.5], device="cuda")
+um = rnd(B, 576, 64, 64)
+cf1, cf2 = torch.relu(rnd(B, 1024, 32, 32)), torch.relu(rnd(B, 1024, 32, 32))
 for rep in range(2):
     t1, t2 = C.tokens_bf16(f1), C.tokens_bf16(f2)
     vol, lv = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_levels=3)
@@ -27,5 +31,10 @@ for rep in range(2):
     o = sb.compute_occlusion(flo, flo, "wang", occlusion_are_zeros=True, threshold=True)
     fw, ov = sb.warp(x6, flo, mul_mask=occ, return_overlap=True)
     mo = sb.preprocess_occlusion_mask(occ)
+    attn = sb.gma.attention(fm, w_qk)
+    agg = sb.gma.aggregate(attn, fm, w_v, gam)
+    del attn
+    up = sb.decoder.upsample_flow(coords - sb.lookup.coords_grid(B, 64, 64, device="cuda"), um)
+    cc = sb.udis2_homography.CCL(cf1, cf2)
     torch.cuda.synchronize()
 print("ok")

@@ -217,6 +217,14 @@ int sb_softmax_rows(float* x, long long rows, int n, long long row_stride, int t
                     sb_stream_t stream);
 int sb_attn_aggregate(const float* attn, const float* v, const float* residual, const float* gamma,
                       float* out, int BH, int Nq, int Nk, int d, sb_stream_t stream);
+/* Opt-in half-traffic variant (not the reference's dtype): sb_softmax_rows_bf16 writes the
+ * probabilities as a dense bf16 matrix [rows, n] (x is left untouched), sb_attn_aggregate_bf16
+ * consumes bf16 attn [BH, Nq, Nk] and bf16 v [BH, d, Nk] (kind::f16 MMA); Nk % 8 == 0. */
+int sb_softmax_rows_bf16(const float* x, void* out_bf16, long long rows, int n, long long row_stride,
+                         sb_stream_t stream);
+int sb_attn_aggregate_bf16(const void* attn_bf16, const void* v_bf16, const float* residual,
+                           const float* gamma, float* out, int BH, int Nq, int Nk, int d,
+                           sb_stream_t stream);
 
 /* D[bh] = A[bh] . B[bh]^T on the TF32 tensor cores (the kernel behind sb_attn_aggregate, row-major
  * output): A [BH, M, K], B [BH, N, K] fp32 K-major, D [BH, M, N] fp32; K % 4 == 0. */

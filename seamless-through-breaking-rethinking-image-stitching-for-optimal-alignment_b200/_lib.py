@@ -47,6 +47,8 @@ SIGNATURES = {
     "sb_gemm_nt_tf32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_ccl_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "sb_ccl": (c_int, [_P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_float, _P]),
+    "sb_softmax_rows_bf16": (c_int, [_P, _P, c_longlong, c_int, c_longlong, _P]),
+    "sb_attn_aggregate_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_upsample_flow": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "sb_range_map": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_morph_open": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

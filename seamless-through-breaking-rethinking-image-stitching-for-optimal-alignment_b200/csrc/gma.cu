@@ -17,6 +17,7 @@
 //    Roofline: HBM — the attention matrix (Nq*Nk*4 B per batch*head) is read once per call; the
 //    reference reads it with an fp32 cuBLAS bmm (FFMA pipe).
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -50,8 +51,10 @@ __device__ __forceinline__ float block_reduce(float v, float* s_red) {
 
 // one CTA (256 threads) per row; the row lives in registers between the passes (n <= 256 * 4 * kMaxVec)
 constexpr int kSoftmaxVec = 8;   // float4 per thread -> rows up to 8192
+template <bool BF16_OUT>
 __global__ void __launch_bounds__(256)
-softmax_rows_kernel(float* __restrict__ x, long long rows, int n, long long row_stride, int to_tf32) {
+softmax_rows_kernel(float* __restrict__ x, long long rows, int n, long long row_stride, int to_tf32,
+                    uint16_t* __restrict__ out_bf16) {
   __shared__ float s_red[8];
   for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
     float* p = x + row * row_stride;
@@ -82,6 +85,12 @@ softmax_rows_kernel(float* __restrict__ x, long long rows, int n, long long row_
       const int c = (i * 256 + threadIdx.x) * 4;
       if (c < n) {
         float4 o = make_float4(v[i].x / sum, v[i].y / sum, v[i].z / sum, v[i].w / sum);
+        if (BF16_OUT) {      // bf16 copy [rows, n] (dense) instead of the in-place fp32 result
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          *reinterpret_cast<uint2*>(out_bf16 + row * (long long)n + c) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+          continue;
+        }
         if (to_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
         *reinterpret_cast<float4*>(p + c) = o;
       }
@@ -98,6 +107,9 @@ constexpr int kGTmemCols = 512;
 
 // instruction descriptor: D = f32, A = B = TF32 (format 2), both K-major, N = 128, M = 128
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) |
+                                ((uint32_t)(GM >> 4) << 24);
+// same with A = B = BF16 (format 1): a K step is then 64 elements (still one 128-byte row)
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GN >> 3) << 17) |
                                 ((uint32_t)(GM >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -125,10 +137,11 @@ struct AttnVParams {
 // MBLK = 128-query blocks per CTA unit: MBLK blocks share each v stage (A: MBLK x 16 KB + B: 16 KB
 // per K step, so v is re-read from L2 MBLK times less often), accumulators = MBLK x 128 TMEM columns,
 // 512 / (MBLK * 128) accumulator sets (MBLK = 4: one set, the epilogue is not overlapped).
-template <int MBLK>
+template <int MBLK, bool BF16>
 __global__ void __launch_bounds__(256, 1)
 attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const AttnVParams p) {
+  constexpr int kKStep = BF16 ? 64 : GK;                       // elements per 128-byte operand row
   constexpr int kStageBytes = (MBLK + 1) * kGBlkBytes;
   constexpr int kStages = kGRingBudget / kStageBytes;          // 6, 4, 2 for MBLK = 1, 2, 4
   constexpr int kAccSets = 4 / MBLK;                           // 4, 2, 1
@@ -180,10 +193,10 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           ptx::mbar_wait(bar_empty + 8 * stage, par ^ 1, 0x21, p.dbg);
           ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);   // rows past Nq / keys past Nk arrive as zeros
           const uint32_t sa = smem_base + stage * kStageBytes;
-          ptx::tma_load_3d(sa + MBLK * kGBlkBytes, &map_b, bar_full + 8 * stage, ks * GK, nt * GN, bh);
+          ptx::tma_load_3d(sa + MBLK * kGBlkBytes, &map_b, bar_full + 8 * stage, ks * kKStep, nt * GN, bh);
 #pragma unroll
           for (int m = 0; m < MBLK; ++m)
-            ptx::tma_load_3d(sa + m * kGBlkBytes, &map_a, bar_full + 8 * stage, ks * GK, (mu * MBLK + m) * GM, bh);
+            ptx::tma_load_3d(sa + m * kGBlkBytes, &map_a, bar_full + 8 * stage, ks * kKStep, (mu * MBLK + m) * GM, bh);
           if (++stage == kStages) { stage = 0; par ^= 1; }
         }
       }
@@ -206,8 +219,10 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int m = 0; m < MBLK; ++m) {
             const uint64_t adesc = ptx::umma_desc_k_sw128(sa + m * kGBlkBytes);
 #pragma unroll
-            for (int k = 0; k < GK / 8; ++k)   // 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
-              umma_tf32(d_tmem + m * GN, adesc + 2 * k, bdesc + 2 * k, kIdescTf32, (ks | k) != 0);
+            for (int k = 0; k < 4; ++k) {      // 8 tf32 / 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
+              if (BF16) ptx::umma_f16(d_tmem + m * GN, adesc + 2 * k, bdesc + 2 * k, kIdescBf16, (ks | k) != 0);
+              else umma_tf32(d_tmem + m * GN, adesc + 2 * k, bdesc + 2 * k, kIdescTf32, (ks | k) != 0);
+            }
           }
           ptx::umma_commit(bar_empty + 8 * stage);      // stage reusable once these MMAs retire
           if (++stage == kStages) { stage = 0; par ^= 1; }
@@ -296,27 +311,49 @@ extern "C" int sb_softmax_rows(float* x, long long rows, int n, long long row_st
              "sb_softmax_rows: n and row_stride must be multiples of 4 floats, x 16-byte aligned");
   SB_REQUIRE(n <= 256 * 4 * kSoftmaxVec, SB_EUNSUP, "sb_softmax_rows: rows longer than %d", 256 * 4 * kSoftmaxVec);
   long long blocks = rows < (long long)kNumSMs * 8 ? rows : (long long)kNumSMs * 8;
-  softmax_rows_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, rows, n, row_stride, to_tf32);
+  softmax_rows_kernel<false><<<(int)blocks, 256, 0, as_stream(stream)>>>(x, rows, n, row_stride, to_tf32, nullptr);
+  SB_LAUNCH_CHECK("softmax_rows_kernel");
+  return SB_OK;
+}
+
+extern "C" int sb_softmax_rows_bf16(const float* x, void* out_bf16, long long rows, int n, long long row_stride,
+                                    sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(rows >= 0 && n >= 0 && row_stride >= n, SB_EINVAL, "sb_softmax_rows_bf16: bad size");
+  if (rows == 0 || n == 0) return SB_OK;
+  SB_REQUIRE(x && out_bf16, SB_EINVAL, "sb_softmax_rows_bf16: null pointer");
+  SB_REQUIRE((n & 3) == 0 && (row_stride & 3) == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0,
+             SB_EUNSUP, "sb_softmax_rows_bf16: n and row_stride must be multiples of 4, x 16-byte / out 8-byte aligned");
+  SB_REQUIRE(n <= 256 * 4 * kSoftmaxVec, SB_EUNSUP, "sb_softmax_rows_bf16: rows longer than %d", 256 * 4 * kSoftmaxVec);
+  long long blocks = rows < (long long)kNumSMs * 8 ? rows : (long long)kNumSMs * 8;
+  softmax_rows_kernel<true><<<(int)blocks, 256, 0, as_stream(stream)>>>(const_cast<float*>(x), rows, n, row_stride, 0,
+                                                                  static_cast<uint16_t*>(out_bf16));
   SB_LAUNCH_CHECK("softmax_rows_kernel");
   return SB_OK;
 }
 
 namespace sb {
-static int launch_attn_v(const CUtensorMap& map_a, const CUtensorMap& map_b, AttnVParams& p, int mblk,
+static int launch_attn_v(const CUtensorMap& map_a, const CUtensorMap& map_b, AttnVParams& p, int mblk, bool bf16,
                          cudaStream_t stream) {
   p.dbg = debug_word_device();
   if (!p.dbg) return SB_ECUDA;
   static bool attr_set = false;
   if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
-    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
-    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
     attr_set = true;
   }
   const int grid = (int)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
-  if (mblk == 4) attn_v_umma_kernel<4><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
-  else if (mblk == 2) attn_v_umma_kernel<2><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
-  else attn_v_umma_kernel<1><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
+  if (bf16) {
+    if (mblk >= 2) attn_v_umma_kernel<2, true><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
+    else attn_v_umma_kernel<1, true><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
+  } else if (mblk == 4) attn_v_umma_kernel<4, false><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
+  else if (mblk == 2) attn_v_umma_kernel<2, false><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
+  else attn_v_umma_kernel<1, false><<<grid, 256, kGSmemTotal, stream>>>(map_a, map_b, p);
   SB_LAUNCH_CHECK("attn_v_umma_kernel");
   return SB_OK;
 }
@@ -349,28 +386,29 @@ extern "C" int sb_gemm_nt_tf32(const float* A, const float* B, float* D, int BH,
   p.NT = (N + GN - 1) / GN; p.ncols = N; p.row_major = 1;
   p.n_units = (long long)BH * p.MU * p.NT;
   p.residual = nullptr; p.gamma = nullptr; p.out = D;
-  return launch_attn_v(map_a, map_b, p, 1, as_stream(stream));
+  return launch_attn_v(map_a, map_b, p, 1, false, as_stream(stream));
 }
 
-extern "C" int sb_attn_aggregate(const float* attn, const float* v, const float* residual,
-                                 const float* gamma, float* out, int BH, int Nq, int Nk, int d,
-                                 sb_stream_t stream) {
-  using namespace sb;
+namespace sb {
+static int attn_aggregate_impl(const void* attn, const void* v, const float* residual, const float* gamma,
+                               float* out, int BH, int Nq, int Nk, int d, bool bf16, sb_stream_t stream) {
   SB_ENTER();
   SB_REQUIRE(BH >= 0 && Nq >= 0 && Nk >= 0 && d >= 0, SB_EINVAL, "sb_attn_aggregate: bad size");
   if (BH == 0 || Nq == 0 || d == 0) return SB_OK;
   SB_REQUIRE(attn && v && out, SB_EINVAL, "sb_attn_aggregate: null pointer");
   SB_REQUIRE(Nk > 0, SB_EINVAL, "sb_attn_aggregate: no keys");
   SB_REQUIRE(d == GN, SB_EUNSUP, "sb_attn_aggregate: dim_head must be %d (got %d)", GN, d);
-  SB_REQUIRE((Nk & 3) == 0 && aligned16(attn) && aligned16(v), SB_EUNSUP,
-             "sb_attn_aggregate: Nk must be a multiple of 4 and attn / v 16-byte aligned (TMA strides)");
+  SB_REQUIRE((Nk & (bf16 ? 7 : 3)) == 0 && aligned16(attn) && aligned16(v), SB_EUNSUP,
+             "sb_attn_aggregate: Nk must be a multiple of %d and attn / v 16-byte aligned (TMA strides)", bf16 ? 8 : 4);
+  const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const int esz = bf16 ? 2 : 4, kstep = bf16 ? 64 : GK;
   CUtensorMap map_a, map_b;
-  int rc = make_map_3d_ex(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, attn, (unsigned long long)Nk,
-                          (unsigned long long)Nq, (unsigned long long)BH, GK, GM, CU_TENSOR_MAP_SWIZZLE_128B,
+  int rc = make_map_3d_ex(&map_a, dt, esz, attn, (unsigned long long)Nk,
+                          (unsigned long long)Nq, (unsigned long long)BH, kstep, GM, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "attn");
   if (rc) return rc;
-  rc = make_map_3d_ex(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v, (unsigned long long)Nk,
-                      (unsigned long long)d, (unsigned long long)BH, GK, GN, CU_TENSOR_MAP_SWIZZLE_128B,
+  rc = make_map_3d_ex(&map_b, dt, esz, v, (unsigned long long)Nk,
+                      (unsigned long long)d, (unsigned long long)BH, kstep, GN, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "v");
   if (rc) return rc;
   const int MB = (Nq + GM - 1) / GM;
@@ -378,13 +416,26 @@ extern "C" int sb_attn_aggregate(const float* attn, const float* v, const float*
   // B=16, N=4096: MBLK 1 / 2 / 4 = 217 / 215 / 237 us — 4 has a single accumulator set, so its
   // epilogue is exposed)
   int mblk = tune_get(SB_TUNE_AGG_MBLK, 0);
-  if (mblk != 1 && mblk != 2 && mblk != 4) mblk = ((long long)BH * ((MB + 1) / 2) >= kNumSMs) ? 2 : 1;
+  if ((mblk != 1 && mblk != 2 && mblk != 4) || (bf16 && mblk == 4)) mblk = ((long long)BH * ((MB + 1) / 2) >= kNumSMs) ? 2 : 1;
   AttnVParams p;
   p.BH = BH; p.Nq = Nq; p.Nk = Nk; p.d = d;
   p.MU = (MB + mblk - 1) / mblk;
-  p.KS = (Nk + GK - 1) / GK;
+  p.KS = (Nk + kstep - 1) / kstep;
   p.NT = 1; p.ncols = d; p.row_major = 0;
   p.n_units = (long long)BH * p.MU;
   p.residual = residual; p.gamma = gamma; p.out = out;
-  return launch_attn_v(map_a, map_b, p, mblk, as_stream(stream));
+  return launch_attn_v(map_a, map_b, p, mblk, bf16, as_stream(stream));
+}
+}  // namespace sb
+
+extern "C" int sb_attn_aggregate(const float* attn, const float* v, const float* residual,
+                                 const float* gamma, float* out, int BH, int Nq, int Nk, int d,
+                                 sb_stream_t stream) {
+  return sb::attn_aggregate_impl(attn, v, residual, gamma, out, BH, Nq, Nk, d, false, stream);
+}
+
+extern "C" int sb_attn_aggregate_bf16(const void* attn_bf16, const void* v_bf16, const float* residual,
+                                      const float* gamma, float* out, int BH, int Nq, int Nk, int d,
+                                      sb_stream_t stream) {
+  return sb::attn_aggregate_impl(attn_bf16, v_bf16, residual, gamma, out, BH, Nq, Nk, d, true, stream);
 }

@@ -45,11 +45,24 @@ def project_qk(fmap, to_qk_weight, heads: int = 1, scale: float | None = None):
     return (scale * q).reshape(b * heads, d, h, w), k.reshape(b * heads, d, h, w)
 
 
-def attention(fmap, to_qk_weight, heads: int = 1, scale: float | None = None):
-    """``Attention.forward`` (gma.py:54-76): fmap ``[b,c,h,w]`` -> attn ``[b, heads, h*w, h*w]`` fp32."""
+def attention(fmap, to_qk_weight, heads: int = 1, scale: float | None = None, dtype=torch.float32):
+    """``Attention.forward`` (gma.py:54-76): fmap ``[b,c,h,w]`` -> attn ``[b, heads, h*w, h*w]``.
+
+    ``dtype=torch.float32`` (default) is the reference's return type. ``dtype=torch.bfloat16`` is an
+    opt-in: the probabilities are stored in bf16, which halves what every ``aggregate`` call (one per
+    GRU iteration) has to read from HBM."""
     b, c, h, w = fmap.shape
     q, k = project_qk(fmap, to_qk_weight, heads, scale)
     n = h * w
+    if dtype == torch.bfloat16:
+        lib = _lib.load()
+        sim = corr_mod.corr(q, k).view(b * heads, n, n)
+        out = torch.empty((b * heads, n, n), dtype=torch.bfloat16, device=sim.device)
+        _lib.check(lib.sb_softmax_rows_bf16(_lib.ptr(sim), _lib.ptr(out), b * heads * n, n, n, _lib.stream_ptr()),
+                   "sb_softmax_rows_bf16")
+        return out.view(b, heads, n, n)
+    if dtype != torch.float32:
+        raise ValueError("attention: dtype must be torch.float32 or torch.bfloat16")
     sim = corr_mod.corr(q, k).view(b * heads, n, n)          # bf16 x bf16 -> fp32 on the tensor cores
     softmax_rows_(sim, to_tf32=True)
     return sim.view(b, heads, n, n)
@@ -61,6 +74,21 @@ def attn_matmul_v(attn, v, residual=None, gamma=None):
     attn ``[BH, Nq, Nk]``, v ``[BH, d, Nk]`` (the conv layout), residual ``[BH, d, Nq]`` or None,
     gamma: 1-element CUDA tensor or None -> ``[BH, d, Nq]``."""
     lib = _lib.load()
+    if attn.dtype == torch.bfloat16:
+        if not attn.is_cuda:
+            raise RuntimeError("attn_matmul_v: stitch_b200 runs on B200 GPUs only (no CPU fallback)")
+        a = attn.contiguous()
+        vv = v.to(torch.bfloat16).contiguous()
+        bh, nq, nk = a.shape
+        d = vv.shape[1]
+        if vv.shape != (bh, d, nk):
+            raise ValueError(f"attn_matmul_v: v {tuple(vv.shape)} does not match attn {tuple(a.shape)}")
+        res = _lib.dev_f32(residual, "residual") if residual is not None else None
+        gm = _lib.dev_f32(gamma, "gamma") if gamma is not None else None
+        out = torch.empty((bh, d, nq), dtype=torch.float32, device=a.device)
+        _lib.check(lib.sb_attn_aggregate_bf16(_lib.ptr(a), _lib.ptr(vv), _lib.ptr(res), _lib.ptr(gm), _lib.ptr(out),
+                                              bh, nq, nk, d, _lib.stream_ptr()), "sb_attn_aggregate_bf16")
+        return out
     a = _lib.dev_f32(attn, "attn")
     vv = _lib.dev_f32(v, "v")
     bh, nq, nk = a.shape
@@ -108,13 +136,14 @@ def aggregate_forward(self, attn, fmap):
 class Attention(nn.Module):
     """Same constructor / parameters as the reference's ``Attention`` (gma.py:35-52)."""
 
-    def __init__(self, *, args=None, dim, max_pos_size=100, heads=4, dim_head=128):
+    def __init__(self, *, args=None, dim, max_pos_size=100, heads=4, dim_head=128, attn_dtype=torch.float32):
         super().__init__()
         self.args, self.heads, self.scale = args, heads, dim_head ** -0.5
         self.to_qk = nn.Conv2d(dim, heads * dim_head * 2, 1, bias=False)
+        self.attn_dtype = attn_dtype
 
     def forward(self, fmap):
-        return attention(fmap, self.to_qk.weight, self.heads, self.scale)
+        return attention(fmap, self.to_qk.weight, self.heads, self.scale, dtype=self.attn_dtype)
 
 
 class Aggregate(nn.Module):

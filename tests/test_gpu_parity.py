@@ -353,6 +353,21 @@ def test_gma_golden(sb):
     assert max_abs(o2, out) == 0.0
 
 
+def test_gma_bf16_attention_option(sb):
+    """Opt-in bf16 probabilities: aggregate within 1e-2 * scale of the fp32 reference, and the kernel
+    within 1e-3 * scale of fp64 on its own bf16 operands."""
+    c = cases.gma_small()
+    g = golden("gma_small")
+    attn = sb.gma.attention(cu(c["fmap"]), cu(c["w_qk"]), heads=1, dtype=torch.bfloat16)
+    assert attn.dtype == torch.bfloat16 and tuple(attn.shape) == g["attn"].shape
+    out = host(sb.gma.aggregate(attn, cu(c["motion"]), cu(c["w_v"]), cu(c["gamma"])))
+    scale = float(np.abs(g["out"]).max())
+    assert max_abs(out, g["out"]) <= 1e-2 * scale
+    v = torch.nn.functional.conv2d(cu(c["motion"]), cu(c["w_v"])).view(2, 128, -1).bfloat16().double()
+    ref = cu(c["motion"]).double() + 0.7 * torch.einsum("bij,bdj->bdi", attn.view(2, 192, 192).double(), v).view(2, 128, 12, 16)
+    assert float((torch.from_numpy(out).cuda().double() - ref).abs().max()) <= 1e-3 * scale
+
+
 def test_gma_full_size_vs_torch(sb):
     """512^2 shape (N = 4096 tokens), batch 2: attn @ v against torch fp32 on the same attention."""
     gen = torch.Generator(device="cuda").manual_seed(71)

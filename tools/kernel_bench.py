@@ -87,6 +87,10 @@ def main():
     ms = timeit(lambda: sb.gma.attn_matmul_v(attn.view(B, n, n), vv, residual=fm.view(B, 128, n), gamma=gam), n=10)
     report("gma attn @ v (tf32 tcgen05)", ms, B * (n * n * 4 + 3 * n * 128 * 4))
     print(f"{'':34s} tensor: {B*2*n*n*128/ms/1e9:.0f} TFLOP/s (tf32)")
+    attn16 = attn.view(B, n, n).bfloat16()
+    ms = timeit(lambda: sb.gma.attn_matmul_v(attn16, vv, residual=fm.view(B, 128, n), gamma=gam), n=10)
+    report("gma attn @ v (bf16 attn opt-in)", ms, B * (n * n * 2 + n * 128 * 2 + 2 * n * 128 * 4))
+    del attn16
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     report("  torch fp32 bmm (reference path)", timeit(lambda: torch.bmm(attn.view(B, n, n), vv.transpose(1, 2)), n=3), B * (n * n * 4 + 2 * n * 128 * 4))

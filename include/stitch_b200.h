@@ -101,6 +101,12 @@ int sb_feat_to_tokens_bf16(const float* fmap, void* tok, int B, int C, int N,
 int sb_corr_tokens(const void* tok1, const void* tok2, float* vol,
                    float* lvl1, float* lvl2, float* lvl3,
                    int B, int C, int H1, int W1, int H2, int W2, sb_stream_t stream);
+/* Same with an explicit row pitch of the volume (in floats, >= H2*W2, a multiple of 4): lets a
+ * caller hold volumes whose token count is not a multiple of 4 in rows padded to the TMA's
+ * 16-byte stride granularity (pad columns are never written; no pyramid in that case). */
+int sb_corr_tokens_pitched(const void* tok1, const void* tok2, float* vol, long long vol_pitch,
+                           float* lvl1, float* lvl2, float* lvl3,
+                           int B, int C, int H1, int W1, int H2, int W2, sb_stream_t stream);
 
 /* Standalone C2: out[p, y, x] = mean of the 2x2 block of in[p] (floor sizes,
  * like F.avg_pool2d(kernel 2, stride 2)).  in [P, H, W] -> out [P, H/2, W/2]. */

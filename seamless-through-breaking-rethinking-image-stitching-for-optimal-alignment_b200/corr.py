@@ -47,6 +47,20 @@ def corr(fmap1: torch.Tensor, fmap2: torch.Tensor, heads: int = 1, pyramid_level
     v2, _, _, h2, w2 = _split_heads(f2, heads)
     bh = b * heads
     n1, n2 = h1 * w1, h2 * w2
+    if n2 % 4 and bh * n1 * n2 > 0:
+        # token count not a multiple of 4 (e.g. 65 x 67 maps): rows padded to the TMA's 16-byte stride
+        # granularity; the result is a strided view with the reference's shape
+        if pyramid_levels:
+            raise ValueError("corr: the fused pyramid needs H2, W2 multiples of 8")
+        n2p = (n2 + 3) // 4 * 4
+        t1 = tokens_bf16(v1.reshape(bh, d, h1, w1))
+        t2 = tokens_bf16(v2.reshape(bh, d, h2, w2))
+        volp = torch.empty((bh, n1, n2p), dtype=torch.float32, device=f1.device)
+        rc = lib.sb_corr_tokens_pitched(_lib.ptr(t1), _lib.ptr(t2), _lib.ptr(volp), n2p, None, None, None,
+                                        bh, d, h1, w1, h2, w2, _lib.stream_ptr())
+        _lib.check(rc, "sb_corr_tokens_pitched")
+        return torch.as_strided(volp, (b, heads, h1, w1, h2, w2),
+                                (heads * n1 * n2p, n1 * n2p, w1 * n2p, n2p, w2, 1))
     vol = torch.empty((bh, n1, n2), dtype=torch.float32, device=f1.device)
     lv = [None, None, None]
     for l in range(pyramid_levels):

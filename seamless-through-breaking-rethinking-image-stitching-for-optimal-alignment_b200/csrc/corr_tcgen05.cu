@@ -435,9 +435,22 @@ extern "C" int sb_avg_pool2x2(const float* in, float* out, long long planes, int
   return SB_OK;
 }
 
+extern "C" int sb_corr_tokens_pitched(const void* tok1, const void* tok2, float* vol, long long vol_pitch,
+                                      float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1,
+                                      int H2, int W2, sb_stream_t stream);
+
 extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, float* lvl1,
                               float* lvl2, float* lvl3, int B, int C, int H1, int W1, int H2,
                               int W2, sb_stream_t stream) {
+  return sb_corr_tokens_pitched(tok1, tok2, vol, (long long)H2 * W2, lvl1, lvl2, lvl3, B, C, H1, W1, H2, W2, stream);
+}
+
+// vol_pitch: row pitch of the volume in floats (>= H2*W2, a multiple of 4): rows of a volume whose
+// token count is not a multiple of 4 are padded by the caller so that the TMA store strides stay
+// 16-byte multiples; the pad columns are never written.
+extern "C" int sb_corr_tokens_pitched(const void* tok1, const void* tok2, float* vol, long long vol_pitch,
+                                      float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1,
+                                      int H2, int W2, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
   SB_REQUIRE(tok1 && tok2 && vol, SB_EINVAL, "sb_corr_tokens: null pointer");
@@ -448,10 +461,13 @@ extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, fl
   const long long N1 = (long long)H1 * W1, N2 = (long long)H2 * W2;
   SB_REQUIRE(N1 < (1 << 30) && N2 < (1 << 30), SB_EUNSUP, "sb_corr_tokens: too many tokens");
   if (B == 0 || N1 == 0 || N2 == 0) return SB_OK;
-  SB_REQUIRE((N2 & 3) == 0, SB_EUNSUP, "sb_corr_tokens: H2*W2 must be a multiple of 4 (TMA row pitch)");
+  SB_REQUIRE(vol_pitch >= N2 && (vol_pitch & 3) == 0, SB_EUNSUP,
+             "sb_corr_tokens: the volume row pitch (%lld floats) must be >= H2*W2 = %lld and a multiple of 4 "
+             "(TMA strides); use sb_corr_tokens_pitched with a padded pitch", vol_pitch, N2);
   SB_REQUIRE(aligned16(tok1) && aligned16(tok2) && aligned16(vol), SB_EINVAL,
              "sb_corr_tokens: pointers must be 16-byte aligned");
   const bool want_pool = lvl1 || lvl2 || lvl3;
+  SB_REQUIRE(!want_pool || vol_pitch == N2, SB_EUNSUP, "sb_corr_tokens: the pyramid needs a dense volume (pitch == H2*W2)");
   if (want_pool)
     SB_REQUIRE((H2 % 8) == 0 && (W2 % 8) == 0, SB_EUNSUP,
                "sb_corr_tokens: pyramid needs H2, W2 multiples of 8 (got %d x %d)", H2, W2);
@@ -465,7 +481,8 @@ extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, fl
   if (rc) return rc;
   rc = make_map_3d(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok2, Cpad, N2, B, BKP, BN, "B");
   if (rc) return rc;
-  rc = make_map_3d(&map_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, vol, N2, N1, B, 32, 32, "V");
+  rc = make_map_3d_ex(&map_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, vol, N2, N1, B, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "V", (unsigned long long)vol_pitch);
   if (rc) return rc;
   map_l1 = map_v;
   if (fused_pool && lvl1) {

@@ -30,11 +30,13 @@ static inline EncodeTiledFn get_encode_fn() {
 static inline int make_map_3d_ex(CUtensorMap* m, CUtensorMapDataType dt, int elt_bytes, const void* base,
                                  unsigned long long d0, unsigned long long d1, unsigned long long d2,
                                  unsigned b0, unsigned b1, CUtensorMapSwizzle swz,
-                                 CUtensorMapL2promotion promo, const char* what) {
+                                 CUtensorMapL2promotion promo, const char* what,
+                                 unsigned long long pitch0 = 0) {   // row pitch in elements (0: dense, = d0)
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return SB_ECUDA;
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * (unsigned long long)elt_bytes, d0 * d1 * (unsigned long long)elt_bytes};
+  const unsigned long long p0 = pitch0 ? pitch0 : d0;
+  cuuint64_t strides[2] = {p0 * (unsigned long long)elt_bytes, p0 * d1 * (unsigned long long)elt_bytes};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr,

@@ -55,6 +55,21 @@ def _corr_check(vol_gpu, f1, f2):
     return err_kernel, err_contract, rms
 
 
+def test_corr_odd_token_count(sb):
+    """13 x 15 = 195 target tokens (not a multiple of 4): pitched volume, strided view of the reference's shape."""
+    gen = torch.Generator().manual_seed(9)
+    f1 = torch.randn(2, 96, 9, 11, generator=gen)
+    f2 = torch.randn(2, 96, 13, 15, generator=gen)
+    vol = sb.corr.corr(cu(f1), cu(f2))
+    assert tuple(vol.shape) == (2, 1, 9, 11, 13, 15)
+    _corr_check(host(vol.contiguous()), f1.numpy(), f2.numpy())
+    # and the lookup on the (copied-contiguous) maps of that volume, generic-width path
+    maps = vol.contiguous().view(2 * 99, 1, 13, 15)
+    coords = sb.lookup.coords_grid(2, 9, 11, device="cuda") + torch.randn(2, 2, 9, 11, device="cuda") * 2
+    out = sb.encode_flow_token(maps, coords)
+    assert_bits_equal(host(out.contiguous()), np.ascontiguousarray(so.encode_flow_token(host(maps), host(coords))), "lookup W2=15")
+
+
 @pytest.mark.parametrize("name", ["corr_c64", "corr_small"])
 def test_corr_small_cases(sb, name):
     c = getattr(cases, name)()

@@ -14,7 +14,8 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint, c_voi
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "libstitchb200.so")
+# STITCH_B200_LIB: load another build of the same library (kernel experiments, tools/)
+LIB_PATH = os.environ.get("STITCH_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libstitchb200.so")
 
 _lock = threading.Lock()
 _lib = None

@@ -85,14 +85,21 @@ feat_to_tokens_bf16_kernel(const float* __restrict__ fmap, uint16_t* __restrict_
 constexpr int BM = 128, BN = 128, BKP = 64;       // tile, K panel (64 bf16 = 128 B)
 constexpr int kMaxPanels = 4;                      // C <= 256
 constexpr int kPanelBytes = BM * 128;              // 16 KB
-constexpr int kStages = 2;
+#ifndef SB_CORR_BSTAGES
+#define SB_CORR_BSTAGES 2
+#endif
+#ifndef SB_CORR_SBUFS
+#define SB_CORR_SBUFS 2
+#endif
+constexpr int kStages = SB_CORR_BSTAGES;
+constexpr int kSBufs = SB_CORR_SBUFS;               // staging buffers per epilogue warp
 constexpr int kTilesPerUnit = 4;
 constexpr int kAccBufs = 4;                        // 4 x 128 TMEM columns
 constexpr int kTmemCols = 512;
 constexpr int kStageBufBytes = 32 * 128;           // per-warp staging: 32 rows x 32 fp32
 constexpr int kSmemA = kMaxPanels * kPanelBytes;                 // 65536
 constexpr int kSmemB = kStages * kMaxPanels * kPanelBytes;       // 131072
-constexpr int kSmemStage = 4 * 2 * kStageBufBytes;               // 32768
+constexpr int kSmemStage = 4 * kSBufs * kStageBufBytes;          // 32768 with 2 buffers per warp
 constexpr int kSmemBar = 256;
 constexpr int kSmemTotal = kSmemA + kSmemB + kSmemStage + kSmemBar + 1024;  // + align slack
 
@@ -226,7 +233,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (warp >= 4) {
     // ================================================================ epilogue
     const int wq = warp - 4;                       // TMEM lane quarter == warp % 4
-    const uint32_t my_stage = sStage + wq * 2 * kStageBufBytes;
+    const uint32_t my_stage = sStage + wq * kSBufs * kStageBufBytes;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
     uint32_t acc = 0, acc_par = 0, sbuf = 0;
     // pooling state (one query row per thread)
@@ -270,7 +277,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
           // staging buffer `sbuf` was last read by the store issued two slices ago
-          if (lane == 0) ptx::tma_store_wait_read<1>();
+          if (lane == 0) ptx::tma_store_wait_read<kSBufs - 1>();
           __syncwarp();
           const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
 #pragma unroll
@@ -287,7 +294,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                               mb * BM + wq * 32, b);
             ptx::tma_store_commit();
           }
-          sbuf ^= 1;
+          if (++sbuf == kSBufs) sbuf = 0;
         }
         // accumulator buffer drained
         ptx::tc_fence_before_sync();
@@ -299,7 +306,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (p.lvl1) {
             // level 1 of this tile = 32 rows x 32 floats per warp: same swizzled staging +
             // TMA store as a volume slice (full 128-byte lines instead of 32 scattered rows)
-            if (lane == 0) ptx::tma_store_wait_read<1>();
+            if (lane == 0) ptx::tma_store_wait_read<kSBufs - 1>();
             __syncwarp();
             const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
 #pragma unroll
@@ -315,7 +322,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               ptx::tma_store_3d(&map_l1, my_stage + sbuf * kStageBufBytes, t * 32, mb * BM + wq * 32, b);
               ptx::tma_store_commit();
             }
-            sbuf ^= 1;
+            if (++sbuf == kSBufs) sbuf = 0;
           }
           // level 2: pool level-1 rows (t even, t odd)
           if ((tt & 1) == 0) {

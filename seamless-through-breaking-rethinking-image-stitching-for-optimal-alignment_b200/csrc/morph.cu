@@ -97,13 +97,28 @@ morph_open_kernel(const float* __restrict__ mask, float* __restrict__ out, int H
 
   // ---- pack: bit = (mask >= 0.5) inside the image, `border` outside
   const uint32_t border = border_is_zero ? 0u : 1u;
-  for (int i = warp; i < rows * kMorphTW; i += (blockDim.x >> 5)) {
-    const int y = i / kMorphTW, w = i - y * kMorphTW;
-    const int gy = y0 + y, gx = x0 + w * 32 + lane;
-    uint32_t bit = border;
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) bit = (ldg_stream(src + (long long)gy * W + gx) >= 0.5f) ? 1u : 0u;
-    const uint32_t word = __ballot_sync(0xffffffffu, bit);
-    if (lane == 0) s_a[i] = word;
+  // 8 row-words per warp and step: 8 independent 128-byte loads in flight before the first ballot
+  // (one load per step left the pack phase latency-bound: 20 warps x 128 B outstanding per SM)
+  constexpr int kPackU = 8;
+  const int n_words = rows * kMorphTW, n_warps = blockDim.x >> 5;
+  for (int i0 = warp; i0 < n_words; i0 += n_warps * kPackU) {
+    float v[kPackU];
+    bool ok[kPackU];
+#pragma unroll
+    for (int u = 0; u < kPackU; ++u) {
+      const int i = i0 + u * n_warps;
+      const int y = i / kMorphTW, w = i - y * kMorphTW;
+      const int gy = y0 + y, gx = x0 + w * 32 + lane;
+      ok[u] = (i < n_words) && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      v[u] = ok[u] ? ldg_stream(src + (long long)gy * W + gx) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kPackU; ++u) {
+      const int i = i0 + u * n_warps;
+      const uint32_t bit = ok[u] ? ((v[u] >= 0.5f) ? 1u : 0u) : border;
+      const uint32_t word = __ballot_sync(0xffffffffu, bit);
+      if (lane == 0 && i < n_words) s_a[i] = word;
+    }
   }
   __syncthreads();
   uint32_t* cur = s_a;

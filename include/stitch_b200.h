@@ -101,6 +101,10 @@ int sb_feat_to_tokens_bf16(const float* fmap, void* tok, int B, int C, int N,
 int sb_corr_tokens(const void* tok1, const void* tok2, float* vol,
                    float* lvl1, float* lvl2, float* lvl3,
                    int B, int C, int H1, int W1, int H2, int W2, sb_stream_t stream);
+/* Opt-in (not the reference's dtype): the volume written as bf16 [B, N1, N2], H2*W2 % 8 == 0 — half
+ * the HBM bytes, which moves the kernel from the write roofline towards the tensor pipe. */
+int sb_corr_tokens_bf16out(const void* tok1, const void* tok2, void* vol_bf16,
+                           int B, int C, int H1, int W1, int H2, int W2, sb_stream_t stream);
 /* Same with an explicit row pitch of the volume (in floats, >= H2*W2, a multiple of 4): lets a
  * caller hold volumes whose token count is not a multiple of 4 in rows padded to the TMA's
  * 16-byte stride granularity (pad columns are never written; no pyramid in that case). */

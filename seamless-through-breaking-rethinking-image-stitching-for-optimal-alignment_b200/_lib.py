@@ -35,6 +35,7 @@ SIGNATURES = {
     "sb_feat_to_tokens_bf16": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "sb_corr_tokens": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_corr_tokens_pitched": (c_int, [_P, _P, _P, c_longlong, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sb_corr_tokens_bf16out": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_avg_pool2x2": (c_int, [_P, _P, c_longlong, c_int, c_int, _P]),
     "sb_corr_lookup": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, _P]),
     "sb_bilinear_sampler": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -112,13 +112,24 @@ def tokens_bf16(fmap: torch.Tensor) -> torch.Tensor:
     return tok
 
 
-def corr_from_tokens(tok1: torch.Tensor, tok2: torch.Tensor, c: int, hw1, hw2, pyramid_levels: int = 0):
+def corr_from_tokens(tok1: torch.Tensor, tok2: torch.Tensor, c: int, hw1, hw2, pyramid_levels: int = 0,
+                     out_dtype=torch.float32):
+    """Volume (+ pyramid) from two token-major bf16 maps. ``out_dtype=torch.bfloat16`` (opt-in, not the
+    reference's dtype; no pyramid) stores the volume in bf16: half the HBM bytes."""
     lib = _lib.load()
     (h1, w1), (h2, w2) = hw1, hw2
     b = tok1.shape[0]
     if tok1.dtype != torch.bfloat16 or tok2.dtype != torch.bfloat16 or not tok1.is_cuda:
         raise RuntimeError("corr_from_tokens: expected CUDA bf16 token maps from tokens_bf16()")
     n1 = h1 * w1
+    if out_dtype == torch.bfloat16:
+        if pyramid_levels:
+            raise ValueError("corr_from_tokens: the bf16 volume has no fused pyramid")
+        vol16 = torch.empty((b, n1, h2 * w2), dtype=torch.bfloat16, device=tok1.device)
+        rc = lib.sb_corr_tokens_bf16out(_lib.ptr(tok1), _lib.ptr(tok2), _lib.ptr(vol16), b, c, h1, w1, h2, w2,
+                                        _lib.stream_ptr())
+        _lib.check(rc, "sb_corr_tokens_bf16out")
+        return vol16.view(b, 1, h1, w1, h2, w2)
     vol = torch.empty((b, n1, h2 * w2), dtype=torch.float32, device=tok1.device)
     lv = [None, None, None]
     for l in range(pyramid_levels):

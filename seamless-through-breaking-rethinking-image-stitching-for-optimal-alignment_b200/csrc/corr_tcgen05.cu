@@ -116,7 +116,9 @@ struct CorrParams {
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                             ((uint32_t)(BM >> 4) << 24);
 
-template <bool POOL>
+// BF16OUT (never with POOL): the volume is written as bf16 [B, N1, N2] — half the bytes, which moves
+// the kernel from the HBM-write roofline towards the tensor pipe (the SURVEY D4 option).
+template <bool POOL, bool BF16OUT = false>
 __global__ void __launch_bounds__(256, 1)
 corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_l1,
@@ -256,6 +258,39 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (t >= t1) break;
         ptx::mbar_wait(bar_t_full + 8 * acc, acc_par, 6, p.dbg);
         ptx::tc_fence_after_sync();
+        if (BF16OUT) {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {          // 64 columns = one 128-byte row of bf16 per query
+            uint32_t r0[32], r1[32], w[32];
+            ptx::tmem_ld_32x32b_x32(lane_taddr + acc * BN + s2 * 64, r0);
+            ptx::tmem_ld_32x32b_x32(lane_taddr + acc * BN + s2 * 64 + 32, r1);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+              __nv_bfloat162 c = __floats2bfloat162_rn(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+              w[j] = *reinterpret_cast<uint32_t*>(&a);
+              w[16 + j] = *reinterpret_cast<uint32_t*>(&c);
+            }
+            if (lane == 0) ptx::tma_store_wait_read<kSBufs - 1>();
+            __syncwarp();
+            const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t a = dst + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * c]),
+                           "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
+                           : "memory");
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_3d(&map_v, my_stage + sbuf * kStageBufBytes, t * BN + s2 * 64, mb * BM + wq * 32, b);
+              ptx::tma_store_commit();
+            }
+            if (++sbuf == kSBufs) sbuf = 0;
+          }
+        } else {
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) {
           uint32_t r[32];
@@ -295,6 +330,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ptx::tma_store_commit();
           }
           if (++sbuf == kSBufs) sbuf = 0;
+        }
         }
         // accumulator buffer drained
         ptx::tc_fence_before_sync();
@@ -455,10 +491,30 @@ extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, fl
 // vol_pitch: row pitch of the volume in floats (>= H2*W2, a multiple of 4): rows of a volume whose
 // token count is not a multiple of 4 are padded by the caller so that the TMA store strides stay
 // 16-byte multiples; the pad columns are never written.
+namespace sb {
+static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, long long vol_pitch, bool bf16_out,
+                            float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1, int H2, int W2,
+                            sb_stream_t stream);
+}
+
 extern "C" int sb_corr_tokens_pitched(const void* tok1, const void* tok2, float* vol, long long vol_pitch,
                                       float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1,
                                       int H2, int W2, sb_stream_t stream) {
-  using namespace sb;
+  return sb::corr_tokens_impl(tok1, tok2, vol, vol_pitch, false, lvl1, lvl2, lvl3, B, C, H1, W1, H2, W2, stream);
+}
+
+// bf16 volume [B, N1, N2] (N2 % 8 == 0): opt-in, not the reference's dtype
+extern "C" int sb_corr_tokens_bf16out(const void* tok1, const void* tok2, void* vol_bf16, int B, int C, int H1,
+                                      int W1, int H2, int W2, sb_stream_t stream) {
+  return sb::corr_tokens_impl(tok1, tok2, vol_bf16, (long long)H2 * W2, true, nullptr, nullptr, nullptr, B, C, H1,
+                              W1, H2, W2, stream);
+}
+
+namespace sb {
+static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, long long vol_pitch, bool bf16_out,
+                            float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1, int H2, int W2,
+                            sb_stream_t stream) {
+  float* vol = static_cast<float*>(vol_any);
   SB_ENTER();
   SB_REQUIRE(tok1 && tok2 && vol, SB_EINVAL, "sb_corr_tokens: null pointer");
   SB_REQUIRE(B >= 0 && C > 0 && H1 >= 0 && W1 >= 0 && H2 >= 0 && W2 >= 0, SB_EINVAL,
@@ -468,6 +524,7 @@ extern "C" int sb_corr_tokens_pitched(const void* tok1, const void* tok2, float*
   const long long N1 = (long long)H1 * W1, N2 = (long long)H2 * W2;
   SB_REQUIRE(N1 < (1 << 30) && N2 < (1 << 30), SB_EUNSUP, "sb_corr_tokens: too many tokens");
   if (B == 0 || N1 == 0 || N2 == 0) return SB_OK;
+  SB_REQUIRE(!bf16_out || (N2 & 7) == 0, SB_EUNSUP, "sb_corr_tokens_bf16out: H2*W2 must be a multiple of 8");
   SB_REQUIRE(vol_pitch >= N2 && (vol_pitch & 3) == 0, SB_EUNSUP,
              "sb_corr_tokens: the volume row pitch (%lld floats) must be >= H2*W2 = %lld and a multiple of 4 "
              "(TMA strides); use sb_corr_tokens_pitched with a padded pitch", vol_pitch, N2);
@@ -488,8 +545,12 @@ extern "C" int sb_corr_tokens_pitched(const void* tok1, const void* tok2, float*
   if (rc) return rc;
   rc = make_map_3d(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok2, Cpad, N2, B, BKP, BN, "B");
   if (rc) return rc;
-  rc = make_map_3d_ex(&map_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, vol, N2, N1, B, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "V", (unsigned long long)vol_pitch);
+  if (bf16_out)
+    rc = make_map_3d_ex(&map_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, vol_any, N2, N1, B, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "V16", (unsigned long long)vol_pitch);
+  else
+    rc = make_map_3d_ex(&map_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, vol, N2, N1, B, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "V", (unsigned long long)vol_pitch);
   if (rc) return rc;
   map_l1 = map_v;
   if (fused_pool && lvl1) {
@@ -522,9 +583,12 @@ extern "C" int sb_corr_tokens_pitched(const void* tok1, const void* tok2, float*
   if (!attr_set) {
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     attr_set = true;
   }
-  if (fused_pool)
+  if (bf16_out)
+    corr_umma_kernel<false, true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, p);
+  else if (fused_pool)
     corr_umma_kernel<true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, p);
   else
     corr_umma_kernel<false><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, p);
@@ -550,6 +614,7 @@ extern "C" int sb_corr_tokens_pitched(const void* tok1, const void* tok2, float*
   }
   return SB_OK;
 }
+}  // namespace sb
 
 extern "C" int sb_corr(const float* fmap1, const float* fmap2, float* vol, float* lvl1, float* lvl2,
                        float* lvl3, void* workspace, size_t workspace_bytes, int B, int C, int H1,

@@ -55,6 +55,20 @@ def _corr_check(vol_gpu, f1, f2):
     return err_kernel, err_contract, rms
 
 
+def test_corr_bf16_volume_option(sb):
+    """Opt-in bf16 volume: equals the fp32 volume of the same kernel rounded to bf16 (round-to-nearest-even)."""
+    gen = torch.Generator().manual_seed(10)
+    f1 = torch.randn(2, 256, 16, 24, generator=gen)
+    f2 = torch.randn(2, 256, 16, 24, generator=gen)
+    t1, t2 = sb.corr.tokens_bf16(cu(f1)), sb.corr.tokens_bf16(cu(f2))
+    v32 = sb.corr.corr_from_tokens(t1, t2, 256, (16, 24), (16, 24))
+    v16 = sb.corr.corr_from_tokens(t1, t2, 256, (16, 24), (16, 24), out_dtype=torch.bfloat16)
+    assert v16.dtype == torch.bfloat16 and v16.shape == v32.shape
+    assert torch.equal(v16, v32.bfloat16())
+    ref = so.corr(f1.numpy(), f2.numpy())
+    assert max_abs(host(v16.float()), ref) <= 1e-2 * float(np.abs(ref).max())
+
+
 def test_corr_odd_token_count(sb):
     """13 x 15 = 195 target tokens (not a multiple of 4): pitched volume, strided view of the reference's shape."""
     gen = torch.Generator().manual_seed(9)

@@ -43,6 +43,11 @@ def main():
         byt = B * (n * n * 4 * (1 + (0.328125 if lv else 0)) + 2 * n * 256 * 2)
         report(f"corr_umma (pyramid levels={lv})", ms, byt)
         print(f"{'':34s} tensor: {B*2*n*n*256/ms/1e9:.0f} TFLOP/s")
+    ms = timeit(lambda: C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), out_dtype=torch.bfloat16))
+    report("corr_umma (bf16 volume, opt-in)", ms, B * (n * n * 2 + 2 * n * 256 * 2))
+    TP = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf = B * 2 * n * n * 256 / ms / 1e9
+    print(f"{'':34s} tensor: {tf:.0f} TFLOP/s = {100*tf/TP.get('bf16_tflops_sustained', 1404.5):.0f}% of sustained / {100*tf/TP.get('bf16_tflops', 1672.2):.0f}% of burst bf16 peak")
     # ---- lookup
     vol = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64))
     maps = vol.view(B * n, 1, 64, 64)

@@ -203,6 +203,33 @@ def test_lookup_cases(sb, name):
         assert max_abs(host(outp.contiguous()), g["out_pyramid"]) <= 1e-5    # pooled maps: torch-GPU pooling order
 
 
+def test_lookup_non_finite_and_extreme_coords(sb):
+    """NaN / +-inf / huge / denormal centres: same values as the oracle (NaN where it is NaN)."""
+    gen = torch.Generator().manual_seed(12)
+    b, h1, w1 = 1, 4, 8
+    maps = torch.randn(b * h1 * w1, 1, 64, 64, generator=gen)
+    coords = torch.rand(b, 2, h1, w1, generator=gen) * 60
+    special = [float("nan"), float("inf"), -float("inf"), 1e30, -1e30, 1e-40, -1e-40, 3e9, -3e9, 63.0, 0.0, -0.0]
+    for i, v in enumerate(special):
+        coords[0, i % 2, (i // 8) % h1, i % w1] = v
+    out = host(sb.encode_flow_token(cu(maps), cu(coords)).contiguous())
+    ref = np.ascontiguousarray(so.encode_flow_token(maps.numpy(), coords.numpy()))
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    assert np.array_equal(np.nan_to_num(out, nan=0.0), np.nan_to_num(ref, nan=0.0))
+
+
+def test_flow_warp_non_finite_flow(sb):
+    gen = torch.Generator().manual_seed(13)
+    x = torch.rand(1, 6, 24, 40, generator=gen) * 255
+    flo = torch.randn(1, 2, 24, 40, generator=gen) * 3
+    for i, v in enumerate([float("nan"), float("inf"), -float("inf"), 1e30, -1e30, 1e-40, 3e9]):
+        flo[0, i % 2, 3 + i, 5 + 2 * i] = v
+    out = host(sb.warp(cu(x), cu(flo)))
+    ref = so.warp(x.numpy(), flo.numpy())
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    assert np.array_equal(np.nan_to_num(out, nan=0.0), np.nan_to_num(ref, nan=0.0))
+
+
 def test_lookup_full_size_vs_oracle(sb):
     """B=16 x 4096 queries on 64x64 maps (config 2); the oracle checks two of the batches."""
     g = torch.Generator(device="cuda").manual_seed(2)

@@ -116,9 +116,19 @@ struct CorrParams {
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                             ((uint32_t)(BM >> 4) << 24);
 
+// instruction descriptor of the CTA-pair MMA: M = 256 across two CTAs
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)((2 * BM) >> 4) << 24);
+
 // BF16OUT (never with POOL): the volume is written as bf16 [B, N1, N2] — half the bytes, which moves
 // the kernel from the HBM-write roofline towards the tensor pipe (the SURVEY D4 option).
-template <bool POOL, bool BF16OUT = false>
+// TWO_CTA: launched as clusters of 2 CTAs (one SM pair); a unit is then 256 queries (CTA r owns rows
+// [256*mbp + 128*r, +128)) and every target tile is ONE tcgen05.mma.cta_group::2 chain issued by the
+// leader CTA: each CTA loads only its half of every B tile (64 target rows, 32 KB instead of 64 KB),
+// all TMA loads signal the leader's barriers, tcgen05.commit multicasts the "stage free" /
+// "accumulator ready" arrivals to both CTAs, both epilogues drain their own TMEM and report back to
+// the leader's "accumulator free" barrier through shared::cluster.
+template <bool POOL, bool BF16OUT = false, bool TWO_CTA = false>
 __global__ void __launch_bounds__(256, 1)
 corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_l1,
@@ -131,15 +141,25 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t sBar = sStage + kSmemStage;
   // barrier map (8 B each)
   const uint32_t bar_a_full = sBar + 0, bar_a_empty = sBar + 8;
-  const uint32_t bar_b_full = sBar + 16;    // [kStages]
-  const uint32_t bar_b_empty = sBar + 32;   // [kStages]
-  const uint32_t bar_t_full = sBar + 48;    // [kAccBufs]
-  const uint32_t bar_t_empty = sBar + 80;   // [kAccBufs]
-  const uint32_t tmem_slot = sBar + 112;    // u32
+  const uint32_t bar_b_full = sBar + 16;    // [<= 4 stages]
+  const uint32_t bar_b_empty = sBar + 48;   // [<= 4 stages]
+  const uint32_t bar_t_full = sBar + 80;    // [kAccBufs]
+  const uint32_t bar_t_empty = sBar + 112;  // [kAccBufs]
+  const uint32_t tmem_slot = sBar + 144;    // u32
+  // CTA-pair mode loads half-size B tiles: the same 128 KB ring holds twice as many stages
+  constexpr int kStages = TWO_CTA ? 2 * sb::kStages : sb::kStages;
+  static_assert(kStages <= 4, "barrier map holds 4 B stages");
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemA + kSmemB + kSmemStage + 112);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemA + kSmemB + kSmemStage + 144);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = TWO_CTA ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  // work is enumerated per cluster in TWO_CTA mode
+  const long long unit0 = TWO_CTA ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long unit_step = TWO_CTA ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  constexpr int kBRows = TWO_CTA ? BN / 2 : BN;                   // B rows this CTA loads per tile
+  constexpr int kBPanelBytes = kBRows * 128;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
@@ -156,43 +176,54 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int a = 0; a < kAccBufs; ++a) {
       ptx::mbar_init(bar_t_full + 8 * a, 1);
-      ptx::mbar_init(bar_t_empty + 8 * a, 4);   // one elected lane per epilogue warp
+      ptx::mbar_init(bar_t_empty + 8 * a, TWO_CTA ? 8 : 4);   // one elected lane per epilogue warp (of both CTAs)
     }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
-    ptx::tmem_relinquish();
+    if (TWO_CTA) { ptx::tmem_alloc_2cta(tmem_slot, kTmemCols); ptx::tmem_relinquish_2cta(); }
+    else { ptx::tmem_alloc(tmem_slot, kTmemCols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (TWO_CTA) ptx::cluster_sync_all();     // the peer's barriers are initialised before anything remote arrives
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const uint32_t panel_tx = (uint32_t)p.KP * kPanelBytes;
+  const uint32_t panel_tx = (uint32_t)p.KP * kPanelBytes;                 // A: this CTA's 128 rows
+  const uint32_t b_tx = (uint32_t)p.KP * kBPanelBytes;                    // B: this CTA's share of a tile
 
   if (warp == 0) {
     // ================================================================ producer
     if (lane == 0) {
       uint32_t a_par = 0, stage = 0, b_par = 0;
-      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      // TWO_CTA: completions of both CTAs' loads are counted on the LEADER's "full" barriers
+      const uint32_t a_full_tgt = TWO_CTA ? ptx::mapa_shared(bar_a_full, 0) : bar_a_full;
+      for (long long u = unit0; u < p.n_units; u += unit_step) {
         const int ng = (int)(u % p.NG);
         const long long r1 = u / p.NG;
-        const int mb = (int)(r1 % p.MB);
+        const int mb = (int)(r1 % p.MB) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
         const int b = (int)(r1 / p.MB);
         ptx::mbar_wait(bar_a_empty, a_par ^ 1, 1, p.dbg);
-        ptx::mbar_arrive_expect_tx(bar_a_full, panel_tx);
-        for (int kp = 0; kp < p.KP; ++kp)
-          ptx::tma_load_3d(sA + kp * kPanelBytes, &map_a, bar_a_full, kp * BKP, mb * BM, b);
+        if (!TWO_CTA) ptx::mbar_arrive_expect_tx(bar_a_full, panel_tx);
+        else if (leader) ptx::mbar_arrive_expect_tx(bar_a_full, 2 * panel_tx);
+        for (int kp = 0; kp < p.KP; ++kp) {
+          if (TWO_CTA) ptx::tma_load_3d_2cta(sA + kp * kPanelBytes, &map_a, a_full_tgt, kp * BKP, mb * BM, b);
+          else ptx::tma_load_3d(sA + kp * kPanelBytes, &map_a, bar_a_full, kp * BKP, mb * BM, b);
+        }
         a_par ^= 1;
         const int t0 = ng * kTilesPerUnit;
         const int t1 = min(t0 + kTilesPerUnit, p.NT);
         for (int t = t0; t < t1; ++t) {
           ptx::mbar_wait(bar_b_empty + 8 * stage, b_par ^ 1, 2, p.dbg);
-          ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, panel_tx);
-          for (int kp = 0; kp < p.KP; ++kp)
-            ptx::tma_load_3d(sB + (stage * kMaxPanels + kp) * kPanelBytes, &map_b,
-                             bar_b_full + 8 * stage, kp * BKP, t * BN, b);
+          if (!TWO_CTA) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, b_tx);
+          else if (leader) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, 2 * b_tx);
+          const uint32_t b_full_tgt = TWO_CTA ? ptx::mapa_shared(bar_b_full + 8 * stage, 0) : bar_b_full + 8 * stage;
+          for (int kp = 0; kp < p.KP; ++kp) {
+            const uint32_t dstb = sB + (stage * kMaxPanels + kp) * kBPanelBytes;
+            if (TWO_CTA) ptx::tma_load_3d_2cta(dstb, &map_b, b_full_tgt, kp * BKP, t * BN + (int)cta_rank * kBRows, b);
+            else ptx::tma_load_3d(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, b);
+          }
           if (++stage == kStages) { stage = 0; b_par ^= 1; }
         }
       }
@@ -200,9 +231,9 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     // ============================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       uint32_t a_par = 0, stage = 0, b_par = 0, acc = 0, acc_par = 0;
-      for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (long long u = unit0; u < p.n_units; u += unit_step) {
         const int ng = (int)(u % p.NG);
         const int t0 = ng * kTilesPerUnit;
         const int t1 = min(t0 + kTilesPerUnit, p.NT);
@@ -216,19 +247,26 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int kp = 0; kp < p.KP; ++kp) {
             const uint64_t adesc = ptx::umma_desc_k_sw128(sA + kp * kPanelBytes);
             const uint64_t bdesc =
-                ptx::umma_desc_k_sw128(sB + (stage * kMaxPanels + kp) * kPanelBytes);
+                ptx::umma_desc_k_sw128(sB + (stage * kMaxPanels + kp) * kBPanelBytes);
 #pragma unroll
             for (int k = 0; k < BKP / 16; ++k) {
               // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
-              ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kp | k) != 0);
+              if (TWO_CTA) ptx::umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc2, (kp | k) != 0);
+              else ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kp | k) != 0);
             }
           }
-          ptx::umma_commit(bar_b_empty + 8 * stage);   // B stage reusable once these MMAs retire
-          ptx::umma_commit(bar_t_full + 8 * acc);      // accumulator ready for the epilogue
+          if (TWO_CTA) {
+            ptx::umma_commit_2cta(bar_b_empty + 8 * stage, 3);   // both CTAs' B stages reusable
+            ptx::umma_commit_2cta(bar_t_full + 8 * acc, 3);      // both CTAs' accumulators ready
+          } else {
+            ptx::umma_commit(bar_b_empty + 8 * stage);   // B stage reusable once these MMAs retire
+            ptx::umma_commit(bar_t_full + 8 * acc);      // accumulator ready for the epilogue
+          }
           if (++stage == kStages) { stage = 0; b_par ^= 1; }
           if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
         }
-        ptx::umma_commit(bar_a_empty);                  // A reusable once the unit's MMAs retire
+        if (TWO_CTA) ptx::umma_commit_2cta(bar_a_empty, 3);
+        else ptx::umma_commit(bar_a_empty);             // A reusable once the unit's MMAs retire
       }
     }
     __syncwarp();
@@ -242,10 +280,10 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float h1[32];   // level-1 partial sums of the current tile (target row pair)
     float h2[16];   // level-2 partial sums across tile pairs
     float h3[8];    // level-3 partial sums across the unit
-    for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    for (long long u = unit0; u < p.n_units; u += unit_step) {
       const int ng = (int)(u % p.NG);
       const long long r1 = u / p.NG;
-      const int mb = (int)(r1 % p.MB);
+      const int mb = (int)(r1 % p.MB) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
       const int b = (int)(r1 / p.MB);
       const int t0 = ng * kTilesPerUnit;
       const int t1 = min(t0 + kTilesPerUnit, p.NT);
@@ -335,7 +373,10 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // accumulator buffer drained
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_t_empty + 8 * acc);
+        if (lane == 0) {
+          if (TWO_CTA) ptx::mbar_arrive_cluster(ptx::mapa_shared(bar_t_empty + 8 * acc, 0));   // the leader's barrier
+          else ptx::mbar_arrive(bar_t_empty + 8 * acc);
+        }
         if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
 
         if (POOL) {
@@ -396,9 +437,11 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (TWO_CTA) ptx::cluster_sync_all();     // neither CTA frees TMEM / exits while its peer still uses the pair
   if (warp == 2) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (TWO_CTA) ptx::tmem_dealloc_2cta(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -543,7 +586,9 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   int rc;
   rc = make_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok1, Cpad, N1, B, BKP, BM, "A");
   if (rc) return rc;
-  rc = make_map_3d(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok2, Cpad, N2, B, BKP, BN, "B");
+  // CTA-pair mode (tcgen05 cta_group::2): every CTA loads half of each B tile
+  const bool two_cta = tune_get(SB_TUNE_CORR_2CTA, 1) == 2;
+  rc = make_map_3d(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok2, Cpad, N2, B, BKP, two_cta ? BN / 2 : BN, "B");
   if (rc) return rc;
   if (bf16_out)
     rc = make_map_3d_ex(&map_v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, vol_any, N2, N1, B, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -569,6 +614,7 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   CorrParams p;
   p.B = B; p.N1 = (int)N1; p.N2 = (int)N2; p.KP = Cpad / 64;
   p.MB = (int)((N1 + BM - 1) / BM);
+  if (two_cta) p.MB = (p.MB + 1) / 2;             // units are pairs of query blocks
   p.NT = (int)((N2 + BN - 1) / BN);
   p.NG = (p.NT + kTilesPerUnit - 1) / kTilesPerUnit;
   p.n_units = (long long)B * p.MB * p.NG;
@@ -584,9 +630,26 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     attr_set = true;
   }
-  if (bf16_out)
+  if (two_cta) {
+    long long clusters = p.n_units < kNumSMs / 2 ? p.n_units : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = kSmemTotal;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (bf16_out) SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<false, true, true>, map_a, map_b, map_v, map_l1, p));
+    else if (fused_pool) SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<true, false, true>, map_a, map_b, map_v, map_l1, p));
+    else SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<false, false, true>, map_a, map_b, map_v, map_l1, p));
+  } else if (bf16_out)
     corr_umma_kernel<false, true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, p);
   else if (fused_pool)
     corr_umma_kernel<true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, p);

@@ -69,6 +69,30 @@ def test_corr_bf16_volume_option(sb):
     assert max_abs(host(v16.float()), ref) <= 1e-2 * float(np.abs(ref).max())
 
 
+def test_corr_cta_pair_mode_is_bit_identical(sb):
+    """tcgen05 cta_group::2 variant (opt-in through sb_tune): same bits as the one-CTA-per-tile kernel,
+    volume and fused pyramid, ragged and full shapes."""
+    lib = sb._lib.load()
+    gen = torch.Generator().manual_seed(14)
+    try:
+        for b, hw, lv in ((1, (9, 20), 0), (2, (64, 64), 3), (1, (24, 40), 0)):
+            f1 = torch.randn(b, 256, *hw, generator=gen)
+            f2 = torch.randn(b, 256, *hw, generator=gen)
+            t1, t2 = sb.corr.tokens_bf16(cu(f1)), sb.corr.tokens_bf16(cu(f2))
+            res = []
+            for mode in (1, 2):
+                lib.sb_tune(6, mode)
+                res.append(sb.corr.corr_from_tokens(t1, t2, 256, hw, hw, pyramid_levels=lv))
+            if lv:
+                assert torch.equal(res[0][0], res[1][0])
+                for x, y in zip(res[0][1], res[1][1]):
+                    assert torch.equal(x, y)
+            else:
+                assert torch.equal(res[0], res[1])
+    finally:
+        lib.sb_tune(6, 0)
+
+
 def test_corr_odd_token_count(sb):
     """13 x 15 = 195 target tokens (not a multiple of 4): pitched volume, strided view of the reference's shape."""
     gen = torch.Generator().manual_seed(9)

@@ -120,6 +120,17 @@ store_kernel(const __grid_constant__ CUtensorMap map32, const __grid_constant__ 
           }
           sbuf ^= 1;
         }
+      } else if (VARIANT == 8 || VARIANT == 9) {
+        constexpr int NB = VARIANT == 8 ? 4 : 8;     // staging buffers per warp (16 / 32 KB in flight per warp)
+        for (int sl = 0; sl < 4; ++sl) {
+          if (lane == 0) wait_read<NB - 1>();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map32, sbase + (warp * NB + sbuf) * 4096, t * 128 + sl * 32, mb * 128 + warp * 32, b);
+            commit();
+          }
+          sbuf = (sbuf + 1) % NB;
+        }
       } else if (VARIANT == 1) {
         if (lane == 0) wait_read<1>();
         __syncwarp();
@@ -162,11 +173,26 @@ int main() {
   enc(&m32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, vol, dims, str, box32, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   enc(&m128, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, vol, dims, str, box128, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   const int smem = 160 * 1024;
+  cudaEvent_t e0_, e1_; cudaEventCreate(&e0_); cudaEventCreate(&e1_);
   cudaFuncSetAttribute(store_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(store_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(store_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(store_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(store_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(store_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(store_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int v = 8; v <= 9; ++v) {
+    for (int i = 0; i < 13; ++i) {
+      if (i == 3) cudaEventRecord(e0_);
+      if (v == 8) store_kernel<8><<<148, 128, smem>>>(m32, m128, vol);
+      else store_kernel<9><<<148, 128, smem>>>(m32, m128, vol);
+    }
+    cudaEventRecord(e1_);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("variant %d: %s\n", v, cudaGetErrorString(e)); return 1; }
+    float ms; cudaEventElapsedTime(&ms, e0_, e1_); ms /= 10;
+    printf("variant %d (%d staging buffers per warp): %7.1f us  %6.0f GB/s\n", v, v == 8 ? 4 : 8, ms * 1e3, (double)B * N * N * 4 / ms / 1e6);
+  }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   {
     float *l1, *l2, *l3;

@@ -132,7 +132,7 @@ template <bool POOL, bool BF16OUT = false, bool TWO_CTA = false>
 __global__ void __launch_bounds__(256, 1)
 corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_l1,
-                 const CorrParams p) {
+                 const __grid_constant__ CUtensorMap map_l2, const CorrParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -279,6 +279,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // pooling state (one query row per thread)
     float h1[32];   // level-1 partial sums of the current tile (target row pair)
     float h2[16];   // level-2 partial sums across tile pairs
+    float h2a[16];  // level-2 row of the unit's first tile pair
     float h3[8];    // level-3 partial sums across the unit
     for (long long u = unit0; u < p.n_units; u += unit_step) {
       const int ng = (int)(u % p.NG);
@@ -409,16 +410,34 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int w = 0; w < 16; ++w)
               h2[w] = fmul(fadd(fadd(h2[w], h1[2 * w]), h1[2 * w + 1]), 0.25f);
-            if (p.lvl2 && row_ok) {
-              float* o = p.lvl2 + (q * p.H2q + (t >> 1)) * 16;
-#pragma unroll
-              for (int c = 0; c < 4; ++c)
-                stg_stream4(o + 4 * c, make_float4(h2[4 * c], h2[4 * c + 1], h2[4 * c + 2], h2[4 * c + 3]));
-            }
             if (tt == 1) {
+#pragma unroll
+              for (int w = 0; w < 16; ++w) h2a[w] = h2[w];       // first level-2 row of the unit: kept for one store
 #pragma unroll
               for (int w = 0; w < 8; ++w) h3[w] = fadd(h2[2 * w], h2[2 * w + 1]);
             } else {  // tt == 3
+              if (p.lvl2) {
+                // the unit's two level-2 rows = 32 floats = one full 128-byte line per query: staged and
+                // TMA-stored like a volume slice (was: 64-byte pieces straight from registers)
+                if (lane == 0) ptx::tma_store_wait_read<kSBufs - 1>();
+                __syncwarp();
+                const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const uint32_t a = dst + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4);
+                  const float* src = (c < 4) ? (h2a + 4 * c) : (h2 + 4 * (c - 4));
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(src[0]), "f"(src[1]),
+                               "f"(src[2]), "f"(src[3])
+                               : "memory");
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  ptx::tma_store_3d(&map_l2, my_stage + sbuf * kStageBufBytes, (t >> 2) * 32, mb * BM + wq * 32, b);
+                  ptx::tma_store_commit();
+                }
+                if (++sbuf == kSBufs) sbuf = 0;
+              }
 #pragma unroll
               for (int w = 0; w < 8; ++w)
                 h3[w] = fmul(fadd(fadd(h3[w], h2[2 * w]), h2[2 * w + 1]), 0.25f);
@@ -582,7 +601,7 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   cudaStream_t s = as_stream(stream);
   const int Cpad = round_up(C, 64);
 
-  CUtensorMap map_a, map_b, map_v, map_l1;
+  CUtensorMap map_a, map_b, map_v, map_l1, map_l2;
   int rc;
   rc = make_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok1, Cpad, N1, B, BKP, BM, "A");
   if (rc) return rc;
@@ -606,6 +625,14 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     if (rc) return rc;
   }
 
+  map_l2 = map_v;
+  if (fused_pool && lvl2) {
+    // lvl2 [B*N1, H2/4, 16] viewed as rows of (H2/4)*16 floats: unit ng owns columns [32 ng, 32 ng + 32)
+    SB_REQUIRE(aligned16(lvl2), SB_EINVAL, "sb_corr_tokens: lvl2 must be 16-byte aligned");
+    rc = make_map_3d(&map_l2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl2, (unsigned long long)(H2 / 4) * 16, N1, B,
+                     32, 32, "L2");
+    if (rc) return rc;
+  }
   unsigned int* g_dbg = debug_word_device();
   if (!g_dbg) {
     return SB_ECUDA;
@@ -646,15 +673,15 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (bf16_out) SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<false, true, true>, map_a, map_b, map_v, map_l1, p));
-    else if (fused_pool) SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<true, false, true>, map_a, map_b, map_v, map_l1, p));
-    else SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<false, false, true>, map_a, map_b, map_v, map_l1, p));
+    if (bf16_out) SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<false, true, true>, map_a, map_b, map_v, map_l1, map_l2, p));
+    else if (fused_pool) SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<true, false, true>, map_a, map_b, map_v, map_l1, map_l2, p));
+    else SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<false, false, true>, map_a, map_b, map_v, map_l1, map_l2, p));
   } else if (bf16_out)
-    corr_umma_kernel<false, true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, p);
+    corr_umma_kernel<false, true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
   else if (fused_pool)
-    corr_umma_kernel<true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, p);
+    corr_umma_kernel<true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
   else
-    corr_umma_kernel<false><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, p);
+    corr_umma_kernel<false><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
   SB_LAUNCH_CHECK("corr_umma_kernel");
 
   if (want_pool && !fused_pool) {

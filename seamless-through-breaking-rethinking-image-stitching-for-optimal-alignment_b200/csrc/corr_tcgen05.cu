@@ -280,6 +280,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float h1[32];   // level-1 partial sums of the current tile (target row pair)
     float h2[16];   // level-2 partial sums across tile pairs
     float h2a[16];  // level-2 row of the unit's first tile pair
+    float h1a[32];  // level-1 row of the even tile of a pair
     float h3[8];    // level-3 partial sums across the unit
     for (long long u = unit0; u < p.n_units; u += unit_step) {
       const int ng = (int)(u % p.NG);
@@ -382,25 +383,37 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
         if (POOL) {
           if (p.lvl1) {
-            // level 1 of this tile = 32 rows x 32 floats per warp: same swizzled staging +
-            // TMA store as a volume slice (full 128-byte lines instead of 32 scattered rows)
-            if (lane == 0) ptx::tma_store_wait_read<kSBufs - 1>();
-            __syncwarp();
-            const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
+            // level 1 of a tile = 32 rows x 32 floats per warp: same swizzled staging + TMA store as a
+            // volume slice. The even tile's row is held in registers (h1a) and stored right before the
+            // odd tile's, so that the two adjacent 128-byte pieces of every query reach L2 / DRAM together.
+            if ((tt & 1) == 0 && t + 1 < t1) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint32_t a = dst + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4);
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(h1[4 * c]),
-                           "f"(h1[4 * c + 1]), "f"(h1[4 * c + 2]), "f"(h1[4 * c + 3])
-                           : "memory");
+              for (int w = 0; w < 32; ++w) h1a[w] = h1[w];
+            } else {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                if (half == 0 && (tt & 1) == 0) continue;          // unpaired last tile: only its own row
+                const float* src = (half == 0) ? h1a : h1;
+                const int tcol = (half == 0) ? t - 1 : t;
+                if (lane == 0) ptx::tma_store_wait_read<kSBufs - 1>();
+                __syncwarp();
+                const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const uint32_t a = dst + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4);
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(src[4 * c]),
+                               "f"(src[4 * c + 1]), "f"(src[4 * c + 2]), "f"(src[4 * c + 3])
+                               : "memory");
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  ptx::tma_store_3d(&map_l1, my_stage + sbuf * kStageBufBytes, tcol * 32, mb * BM + wq * 32, b);
+                  ptx::tma_store_commit();
+                }
+                if (++sbuf == kSBufs) sbuf = 0;
+              }
             }
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              ptx::tma_store_3d(&map_l1, my_stage + sbuf * kStageBufBytes, t * 32, mb * BM + wq * 32, b);
-              ptx::tma_store_commit();
-            }
-            if (++sbuf == kSBufs) sbuf = 0;
           }
           // level 2: pool level-1 rows (t even, t odd)
           if ((tt & 1) == 0) {

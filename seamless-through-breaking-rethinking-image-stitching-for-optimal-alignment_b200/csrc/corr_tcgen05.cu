@@ -128,7 +128,11 @@ constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN
 // all TMA loads signal the leader's barriers, tcgen05.commit multicasts the "stage free" /
 // "accumulator ready" arrivals to both CTAs, both epilogues drain their own TMEM and report back to
 // the leader's "accumulator free" barrier through shared::cluster.
-template <bool POOL, bool BF16OUT = false, bool TWO_CTA = false>
+// POOL: 0 = volume only; 1 = fused pyramid for W2 == 64 (a 128-column tile is two target rows);
+// 2 = fused pyramid for W2 == 128 (a tile is ONE target row: the epilogue drains tile PAIRS, reading
+// both rows' accumulators from TMEM slice by slice, so level 1 needs no cross-tile carry; units are
+// 8 tiles = 8 target rows so that level 3 closes inside the unit).
+template <int POOL, bool BF16OUT = false, bool TWO_CTA = false>
 __global__ void __launch_bounds__(256, 1)
 corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_l1,
@@ -158,6 +162,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // work is enumerated per cluster in TWO_CTA mode
   const long long unit0 = TWO_CTA ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
   const long long unit_step = TWO_CTA ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  constexpr int kTPU = (POOL == 2) ? 8 : kTilesPerUnit;          // tiles per unit
   constexpr int kBRows = TWO_CTA ? BN / 2 : BN;                   // B rows this CTA loads per tile
   constexpr int kBPanelBytes = kBRows * 128;
 
@@ -165,7 +170,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_b);
     ptx::prefetch_tensormap(&map_v);
-    if (POOL) ptx::prefetch_tensormap(&map_l1);
+    if (POOL) { ptx::prefetch_tensormap(&map_l1); ptx::prefetch_tensormap(&map_l2); }
   }
   if (warp == 1 && lane == 0) {
     ptx::mbar_init(bar_a_full, 1);
@@ -212,8 +217,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           else ptx::tma_load_3d(sA + kp * kPanelBytes, &map_a, bar_a_full, kp * BKP, mb * BM, b);
         }
         a_par ^= 1;
-        const int t0 = ng * kTilesPerUnit;
-        const int t1 = min(t0 + kTilesPerUnit, p.NT);
+        const int t0 = ng * kTPU;
+        const int t1 = min(t0 + kTPU, p.NT);
         for (int t = t0; t < t1; ++t) {
           ptx::mbar_wait(bar_b_empty + 8 * stage, b_par ^ 1, 2, p.dbg);
           if (!TWO_CTA) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, b_tx);
@@ -235,8 +240,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t a_par = 0, stage = 0, b_par = 0, acc = 0, acc_par = 0;
       for (long long u = unit0; u < p.n_units; u += unit_step) {
         const int ng = (int)(u % p.NG);
-        const int t0 = ng * kTilesPerUnit;
-        const int t1 = min(t0 + kTilesPerUnit, p.NT);
+        const int t0 = ng * kTPU;
+        const int t1 = min(t0 + kTPU, p.NT);
         ptx::mbar_wait(bar_a_full, a_par, 3, p.dbg);
         a_par ^= 1;
         for (int t = t0; t < t1; ++t) {
@@ -287,11 +292,112 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const long long r1 = u / p.NG;
       const int mb = (int)(r1 % p.MB) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
       const int b = (int)(r1 / p.MB);
-      const int t0 = ng * kTilesPerUnit;
-      const int t1 = min(t0 + kTilesPerUnit, p.NT);
+      const int t0 = ng * kTPU;
+      const int t1 = min(t0 + kTPU, p.NT);
       const int row = mb * BM + wq * 32 + lane;    // query index within the batch
       const bool row_ok = row < p.N1;
       const long long q = (long long)b * p.N1 + row;
+      if (POOL == 2) {
+        // ---------------------------------------------------------- W2 == 128: tile pairs
+        // staged 32 x 128-byte block -> one TMA store (volume slice, level-1 half row, level-2 row)
+        auto stage_store = [&](const CUtensorMap* map, const uint32_t* w, int c0, int r0) {
+          if (lane == 0) ptx::tma_store_wait_read<kSBufs - 1>();
+          __syncwarp();
+          const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t a = dst + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * c]), "r"(w[4 * c + 1]),
+                         "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
+                         : "memory");
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_3d(map, my_stage + sbuf * kStageBufBytes, c0, r0, b);
+            ptx::tma_store_commit();
+          }
+          if (++sbuf == kSBufs) sbuf = 0;
+        };
+        const int r0 = mb * BM + wq * 32;
+        float g2[32], g2a[32], g3[16];               // level-2 partial / first row of the unit, level-3 partial
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {             // pair pp = target rows t0 + 2pp, t0 + 2pp + 1
+          const int t = t0 + 2 * pp;
+          if (t >= t1) break;
+          const uint32_t accA = acc, parA = acc_par;
+          if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
+          const uint32_t accB = acc, parB = acc_par;
+          if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
+          ptx::mbar_wait(bar_t_full + 8 * accA, parA, 6, p.dbg);
+          ptx::mbar_wait(bar_t_full + 8 * accB, parB, 7, p.dbg);
+          ptx::tc_fence_after_sync();
+          uint32_t l1w[32];                          // level-1 values of two slices = 32 floats = 128 bytes
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            uint32_t ra[32], rb[32];
+            ptx::tmem_ld_32x32b_x32(lane_taddr + accA * BN + sl * 32, ra);
+            ptx::tmem_ld_32x32b_x32(lane_taddr + accB * BN + sl * 32, rb);
+            ptx::tmem_ld_wait();
+            // avg_pool2d order: ((a00 + a01) + a10) + a11, then * 0.25
+#pragma unroll
+            for (int w = 0; w < 16; ++w)
+              l1w[(sl & 1) * 16 + w] = __float_as_uint(fmul(
+                  fadd(fadd(fadd(__uint_as_float(ra[2 * w]), __uint_as_float(ra[2 * w + 1])), __uint_as_float(rb[2 * w])),
+                       __uint_as_float(rb[2 * w + 1])), 0.25f));
+            stage_store(&map_v, ra, t * BN + sl * 32, r0);
+            stage_store(&map_v, rb, (t + 1) * BN + sl * 32, r0);
+            if (sl & 1) {
+              // level-1 row (t0/2 + pp) of every query: 64 floats, this half = columns [32*(sl>>1), +32)
+              if (p.lvl1) stage_store(&map_l1, l1w, ((t >> 1)) * 64 + (sl >> 1) * 32, r0);
+              // level 2: horizontal pairs of level 1 now, vertical pair with the next level-1 row later
+#pragma unroll
+              for (int w = 0; w < 16; ++w) {
+                const float hsum = fadd(__uint_as_float(l1w[2 * w]), __uint_as_float(l1w[2 * w + 1]));
+                const int i2 = (sl >> 1) * 16 + w;
+                if ((pp & 1) == 0) g2[i2] = hsum;
+                else g2[i2] = fmul(fadd(fadd(g2[i2], __uint_as_float(l1w[2 * w])), __uint_as_float(l1w[2 * w + 1])), 0.25f);
+              }
+            }
+          }
+          // both accumulators drained
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if (TWO_CTA) {
+              ptx::mbar_arrive_cluster(ptx::mapa_shared(bar_t_empty + 8 * accA, 0));
+              ptx::mbar_arrive_cluster(ptx::mapa_shared(bar_t_empty + 8 * accB, 0));
+            } else {
+              ptx::mbar_arrive(bar_t_empty + 8 * accA);
+              ptx::mbar_arrive(bar_t_empty + 8 * accB);
+            }
+          }
+          if (pp & 1) {
+            // a level-2 row (32 floats = one 128-byte line per query) is complete
+            if (p.lvl2) {
+              uint32_t w2[32];
+#pragma unroll
+              for (int w = 0; w < 32; ++w) w2[w] = __float_as_uint(g2[w]);
+              stage_store(&map_l2, w2, (t >> 2) * 32, r0);
+            }
+            if (pp == 1) {
+#pragma unroll
+              for (int w = 0; w < 16; ++w) g3[w] = fadd(g2[2 * w], g2[2 * w + 1]);
+            } else {
+#pragma unroll
+              for (int w = 0; w < 16; ++w) g3[w] = fmul(fadd(fadd(g3[w], g2[2 * w]), g2[2 * w + 1]), 0.25f);
+              if (p.lvl3 && row_ok) {
+                float* o = p.lvl3 + (q * p.H2e + (t >> 3)) * 16;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  stg_stream4(o + 4 * c, make_float4(g3[4 * c], g3[4 * c + 1], g3[4 * c + 2], g3[4 * c + 3]));
+              }
+            }
+          }
+        }
+        (void)g2a;
+        continue;
+      }
 #pragma unroll
       for (int tt = 0; tt < kTilesPerUnit; ++tt) {
         const int t = t0 + tt;
@@ -336,7 +442,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(lane_taddr + acc * BN + sl * 32, r);
           ptx::tmem_ld_wait();
-          if (POOL) {
+          if (POOL == 1) {
             // W2 == 64: slices 0,1 = target row 2t (w 0..31, 32..63); 2,3 = row 2t+1.
             // avg_pool2d order: ((a00 + a01) + a10) + a11, then * 0.25
             const int hb = (sl & 1) * 16;
@@ -381,7 +487,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
 
-        if (POOL) {
+        if (POOL == 1) {
           if (p.lvl1) {
             // level 1 of a tile = 32 rows x 32 floats per warp: same swizzled staging + TMA store as a
             // volume slice. The even tile's row is held in registers (h1a) and stored right before the
@@ -610,7 +716,8 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   if (want_pool)
     SB_REQUIRE((H2 % 8) == 0 && (W2 % 8) == 0, SB_EUNSUP,
                "sb_corr_tokens: pyramid needs H2, W2 multiples of 8 (got %d x %d)", H2, W2);
-  const bool fused_pool = want_pool && W2 == 64;
+  const int pool_mode = !want_pool ? 0 : (W2 == 64 ? 1 : (W2 == 128 ? 2 : 0));
+  const bool fused_pool = pool_mode != 0;
   cudaStream_t s = as_stream(stream);
   const int Cpad = round_up(C, 64);
 
@@ -619,7 +726,8 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   rc = make_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok1, Cpad, N1, B, BKP, BM, "A");
   if (rc) return rc;
   // CTA-pair mode (tcgen05 cta_group::2): every CTA loads half of each B tile
-  const bool two_cta = tune_get(SB_TUNE_CORR_2CTA, 1) == 2;
+  const bool two_cta = tune_get(SB_TUNE_CORR_2CTA, 1) == 2 && !(lvl1 || lvl2 || lvl3) ? true
+                       : (tune_get(SB_TUNE_CORR_2CTA, 1) == 2 && W2 == 64);   // the W2 == 128 pyramid runs one CTA per tile
   rc = make_map_3d(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok2, Cpad, N2, B, BKP, two_cta ? BN / 2 : BN, "B");
   if (rc) return rc;
   if (bf16_out)
@@ -633,7 +741,7 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   if (fused_pool && lvl1) {
     // lvl1 [B*N1, H2/2, 32] viewed as rows of (H2/2)*32 floats: tile t owns columns [32t, 32t+32)
     SB_REQUIRE(aligned16(lvl1), SB_EINVAL, "sb_corr_tokens: lvl1 must be 16-byte aligned");
-    rc = make_map_3d(&map_l1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl1, (unsigned long long)(H2 / 2) * 32, N1, B,
+    rc = make_map_3d(&map_l1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl1, (unsigned long long)(H2 / 2) * (W2 / 2), N1, B,
                      32, 32, "L1");
     if (rc) return rc;
   }
@@ -642,7 +750,7 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   if (fused_pool && lvl2) {
     // lvl2 [B*N1, H2/4, 16] viewed as rows of (H2/4)*16 floats: unit ng owns columns [32 ng, 32 ng + 32)
     SB_REQUIRE(aligned16(lvl2), SB_EINVAL, "sb_corr_tokens: lvl2 must be 16-byte aligned");
-    rc = make_map_3d(&map_l2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl2, (unsigned long long)(H2 / 4) * 16, N1, B,
+    rc = make_map_3d(&map_l2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lvl2, (unsigned long long)(H2 / 4) * (W2 / 4), N1, B,
                      32, 32, "L2");
     if (rc) return rc;
   }
@@ -656,7 +764,8 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   p.MB = (int)((N1 + BM - 1) / BM);
   if (two_cta) p.MB = (p.MB + 1) / 2;             // units are pairs of query blocks
   p.NT = (int)((N2 + BN - 1) / BN);
-  p.NG = (p.NT + kTilesPerUnit - 1) / kTilesPerUnit;
+  const int tpu = (pool_mode == 2) ? 8 : kTilesPerUnit;
+  p.NG = (p.NT + tpu - 1) / tpu;
   p.n_units = (long long)B * p.MB * p.NG;
   p.H2h = H2 / 2; p.H2q = H2 / 4; p.H2e = H2 / 8;
   p.lvl1 = fused_pool ? lvl1 : nullptr;
@@ -667,12 +776,13 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   const int grid = (int)((p.n_units < kNumSMs) ? p.n_units : kNumSMs);
   static bool attr_set = false;
   if (!attr_set) {
-    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     attr_set = true;
   }
   if (two_cta) {
@@ -686,15 +796,17 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (bf16_out) SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<false, true, true>, map_a, map_b, map_v, map_l1, map_l2, p));
-    else if (fused_pool) SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<true, false, true>, map_a, map_b, map_v, map_l1, map_l2, p));
-    else SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<false, false, true>, map_a, map_b, map_v, map_l1, map_l2, p));
+    if (bf16_out) SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<0, true, true>, map_a, map_b, map_v, map_l1, map_l2, p));
+    else if (fused_pool) SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<1, false, true>, map_a, map_b, map_v, map_l1, map_l2, p));
+    else SB_CUDA(cudaLaunchKernelEx(&cfg, corr_umma_kernel<0, false, true>, map_a, map_b, map_v, map_l1, map_l2, p));
   } else if (bf16_out)
-    corr_umma_kernel<false, true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
+    corr_umma_kernel<0, true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
+  else if (pool_mode == 2)
+    corr_umma_kernel<2><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
   else if (fused_pool)
-    corr_umma_kernel<true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
+    corr_umma_kernel<1><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
   else
-    corr_umma_kernel<false><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
+    corr_umma_kernel<0><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
   SB_LAUNCH_CHECK("corr_umma_kernel");
 
   if (want_pool && !fused_pool) {

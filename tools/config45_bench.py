@@ -20,7 +20,7 @@ for B in (1, 2):
     report(f"corr_umma 1024^2 B={B}", ms, B * (n * n * 4 + 2 * n * 256 * 2))
     print(f"{'':34s} tensor: {B*2*n*n*256/ms/1e9:.0f} TFLOP/s")
     ms = timeit(lambda: C.corr_from_tokens(t1, t2, 256, (128, 128), (128, 128), pyramid_levels=3), n=3)
-    report(f"  + chained 3-level pyramid B={B}", ms, B * (n * n * 4 * (1 + 2 * 0.328125) + 2 * n * 256 * 2))
+    report(f"  + fused 3-level pyramid B={B}", ms, B * (n * n * 4 * 1.328125 + 2 * n * 256 * 2))
     vol = C.corr_from_tokens(t1, t2, 256, (128, 128), (128, 128))
     coords = sb.lookup.coords_grid(B, 128, 128, device="cuda") + rnd(B, 2, 128, 128) * 2
     ms = timeit(lambda: sb.encode_flow_token(vol.view(B * n, 1, 128, 128), coords), n=10)

@@ -265,7 +265,7 @@ def run_ours(args):
         last_out = lambda: sp.slots[(sp.i - 1) % sp.depth]["out"]
     else:
         out_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
-                    for k in ("final_warp_output", "overlap", "origin_occlusion_mask")}
+                    for k in ("warped_image_pred", "valid")}
         h2d = pb_host.nbytes()
         d2h = sum(h.numel() * h.element_size() for h in out_host.values())
         keep = {}
@@ -298,7 +298,7 @@ def run_ours(args):
 
     # ---------------- the single collective of the path: final metric reduction
     # (computed from the results that arrived in pinned HOST memory)
-    metric_sum = torch.tensor([host_result["final_warp_output"].double().mean().item(), float(B)],
+    metric_sum = torch.tensor([host_result["warped_image_pred"].double().mean().item(), float(B)],
                               dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(metric_sum, op=dist.ReduceOp.SUM)
@@ -357,7 +357,7 @@ def run_ours(args):
                             else "serial H2D -> step -> D2H on one stream")},
             "gpu_launches": launches,
             "clocks": clocks,
-            "reduced_metric": {"mean_final_warp": metric_sum[0].item() / world, "pairs": metric_sum[1].item()},
+            "reduced_metric": {"mean_warped_image": metric_sum[0].item() / world, "pairs": metric_sum[1].item()},
         }
         print(json.dumps(line), flush=True)
     if distributed:

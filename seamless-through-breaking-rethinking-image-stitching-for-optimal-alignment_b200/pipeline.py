@@ -167,8 +167,12 @@ class HotPath:
         occ = warp_utils.compute_occlusion(pb.flow_ij, pb.flow_ji, "wang", occlusion_are_zeros=True,
                                            boundaries_occluded=True, threshold=True)
         final_warp, overlap = warp_utils.warp(output_H, pb.flow_ij, mul_mask=occ, return_overlap=True)
+        # what the reference's evaluation takes to the host (evaluate.py:43-50): the warped image and the
+        # channel mean of its warped ones-mask
+        warped_image_pred = final_warp[:, 0:3].contiguous()
+        valid = final_warp[:, 3:6].mean(dim=1, keepdim=True)
         return dict(final_warp_output=final_warp, overlap=overlap, origin_occlusion_mask=occ,
-                    output_H=output_H, output_H_inv=output_H_inv)
+                    output_H=output_H, output_H_inv=output_H_inv, warped_image_pred=warped_image_pred, valid=valid)
 
     def _cost_stage(self, pb: PairBatch):
         size, iters = self.size, self.iters
@@ -225,7 +229,8 @@ class StreamedHotPath:
     (``evaluate.py:43-53``) for the hot path.
     """
 
-    RESULT_KEYS = ("final_warp_output", "overlap", "origin_occlusion_mask")
+    # the tensors evaluate.py:47-50 calls .cpu() on
+    RESULT_KEYS = ("warped_image_pred", "valid")
 
     def __init__(self, template: PairBatch, size: int = 512, iters: int = 12, pyramid: bool = True,
                  device=None, depth: int = 2):

@@ -237,6 +237,8 @@ class StreamedHotPath:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.depth = depth
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        # a second host->device stream: the large input tensors are split over two copy engines
+        self.s_in2 = torch.cuda.Stream(self.device)
         self.slots = []
         for _ in range(depth):
             hp = HotPath(size=size, iters=iters, pyramid=pyramid)
@@ -247,8 +249,8 @@ class StreamedHotPath:
                 out = hp.capture(dev_in)
             host_out = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in self.RESULT_KEYS}
             self.slots.append(dict(hp=hp, dev_in=dev_in, out=out, host_out=host_out,
-                                   in_ready=torch.cuda.Event(), run_done=torch.cuda.Event(),
-                                   out_done=torch.cuda.Event()))
+                                   in_ready=torch.cuda.Event(), in_ready2=torch.cuda.Event(),
+                                   run_done=torch.cuda.Event(), out_done=torch.cuda.Event()))
         torch.cuda.synchronize(self.device)
         self.i = 0
 
@@ -263,13 +265,16 @@ class StreamedHotPath:
         valid after ``slot['out_done'].synchronize()`` / ``drain()``."""
         sl = self.slots[self.i % self.depth]
         self.i += 1
-        with torch.cuda.stream(self.s_in):
-            self.s_in.wait_event(sl["run_done"])          # the previous user of these inputs has run
-            for d, h in zip(sl["dev_in"].tensors(), pb_host.tensors()):
-                d.copy_(h, non_blocking=True)
-            sl["in_ready"].record(self.s_in)
+        pairs = list(zip(sl["dev_in"].tensors(), pb_host.tensors()))
+        for stream, ev, part in ((self.s_in, sl["in_ready"], pairs[0::2]), (self.s_in2, sl["in_ready2"], pairs[1::2])):
+            with torch.cuda.stream(stream):
+                stream.wait_event(sl["run_done"])         # the previous user of these inputs has run
+                for d, h in part:
+                    d.copy_(h, non_blocking=True)
+                ev.record(stream)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(sl["in_ready"])
+            self.s_run.wait_event(sl["in_ready2"])
             self.s_run.wait_event(sl["out_done"])         # its previous results have left the device
             sl["hp"].replay()
             sl["run_done"].record(self.s_run)
@@ -283,15 +288,15 @@ class StreamedHotPath:
     def join(self, stream=None):
         """Make ``stream`` (default: current) wait for everything submitted so far."""
         stream = torch.cuda.current_stream(self.device) if stream is None else stream
-        for s in (self.s_in, self.s_run, self.s_out):
+        for s in (self.s_in, self.s_in2, self.s_run, self.s_out):
             stream.wait_stream(s)
 
     def fork(self, stream=None):
         """Order all three internal streams after ``stream`` (default: current)."""
         stream = torch.cuda.current_stream(self.device) if stream is None else stream
-        for s in (self.s_in, self.s_run, self.s_out):
+        for s in (self.s_in, self.s_in2, self.s_run, self.s_out):
             s.wait_stream(stream)
 
     def drain(self):
-        for s in (self.s_in, self.s_run, self.s_out):
+        for s in (self.s_in, self.s_in2, self.s_run, self.s_out):
             s.synchronize()

@@ -106,8 +106,12 @@ class HotPath:
     """Runs the step on the current CUDA device through the package's public,
     reference-shaped functions (the same calls a patched reference makes)."""
 
-    def __init__(self, size: int = 512, iters: int = 12, pyramid: bool = True, r: int = 4, overlap: bool = True):
+    def __init__(self, size: int = 512, iters: int = 12, pyramid: bool = True, r: int = 4, overlap: bool = True,
+                 eval_outputs: bool = False):
         self.size, self.iters, self.pyramid, self.r = size, iters, pyramid, r
+        # eval_outputs: also produce the two tensors the reference's evaluation takes to the host
+        # (evaluate.py:43-50) — used by the host-buffer pipeline, not part of the hot path itself
+        self.eval_outputs = eval_outputs
         # overlap: the warp stage (homography warps, occlusion, flow warp: instruction-bound gathers)
         # does not depend on the cost-volume stage (HBM-bound), so it runs on a second stream and
         # the GPU co-schedules the two; inside a captured graph this is a fork/join of two branches.
@@ -167,12 +171,14 @@ class HotPath:
         occ = warp_utils.compute_occlusion(pb.flow_ij, pb.flow_ji, "wang", occlusion_are_zeros=True,
                                            boundaries_occluded=True, threshold=True)
         final_warp, overlap = warp_utils.warp(output_H, pb.flow_ij, mul_mask=occ, return_overlap=True)
-        # what the reference's evaluation takes to the host (evaluate.py:43-50): the warped image and the
-        # channel mean of its warped ones-mask
-        warped_image_pred = final_warp[:, 0:3].contiguous()
-        valid = final_warp[:, 3:6].mean(dim=1, keepdim=True)
-        return dict(final_warp_output=final_warp, overlap=overlap, origin_occlusion_mask=occ,
-                    output_H=output_H, output_H_inv=output_H_inv, warped_image_pred=warped_image_pred, valid=valid)
+        out = dict(final_warp_output=final_warp, overlap=overlap, origin_occlusion_mask=occ,
+                   output_H=output_H, output_H_inv=output_H_inv)
+        if self.eval_outputs:
+            # what the reference's evaluation takes to the host (evaluate.py:43-50): the warped image and
+            # the channel mean of its warped ones-mask
+            out["warped_image_pred"] = final_warp[:, 0:3].contiguous()
+            out["valid"] = final_warp[:, 3:6].mean(dim=1, keepdim=True)
+        return out
 
     def _cost_stage(self, pb: PairBatch):
         size, iters = self.size, self.iters
@@ -241,7 +247,7 @@ class StreamedHotPath:
         self.s_in2 = torch.cuda.Stream(self.device)
         self.slots = []
         for _ in range(depth):
-            hp = HotPath(size=size, iters=iters, pyramid=pyramid)
+            hp = HotPath(size=size, iters=iters, pyramid=pyramid, eval_outputs=True)
             dev_in = template.map(lambda t: torch.empty_like(t, device=self.device))
             for d, h in zip(dev_in.tensors(), template.tensors()):
                 d.copy_(h)

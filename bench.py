@@ -178,7 +178,9 @@ def run_ours(args):
 
     B = BATCH_PER_GPU
     # rank r owns pairs [r*B, (r+1)*B) of the global list (weak scaling, no data-path collective)
-    pb_host = make_pair_batch(rank * B, B, size=SIZE, iters=ITERS).map(lambda t: t.pin_memory())
+    # pinned host staging buffers (--wc: write-combined, filled once by the CPU, read by the device)
+    pb_host = make_pair_batch(rank * B, B, size=SIZE, iters=ITERS).map(
+        (lambda t: _lib.pinned_like(t, write_combined=True)) if args.wc else (lambda t: t.pin_memory()))
     pb_dev = pb_host.map(lambda t: t.to(dev, non_blocking=True))
     hp = HotPath(size=SIZE, iters=ITERS, pyramid=True, overlap=args.overlap, eval_outputs=not args.graph)
     stream = torch.cuda.current_stream()
@@ -376,6 +378,7 @@ def main():
                     help="eager launches instead of replaying the step as one captured CUDA graph")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="run the warp stage after the cost-volume stage instead of on a second stream")
+    ap.add_argument("--wc", action="store_true", help="write-combined pinned host input buffers (experiment)")
     ap.set_defaults(graph=True, overlap=True)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -51,6 +51,10 @@ int sb_device_check(void);
  * (bench.py's "gpu_launches"). */
 long long sb_launch_count(void);
 void sb_reset_launch_count(void);
+/* Pinned (page-locked, portable) host buffers for the host-resident data path; write_combined != 0
+ * adds cudaHostAllocWriteCombined (CPU fills sequentially, device reads). NULL on failure. */
+void* sb_host_alloc(size_t bytes, int write_combined);
+int sb_host_free(void* p);
 /* Tuning knobs for kernel experiments (tools/, bench sweeps). value 0 restores
  * the built-in default. Never changes results, only launch geometry (except the
  * knobs marked EXPERIMENT ONLY, which no product path sets). */

@@ -30,6 +30,8 @@ SIGNATURES = {
     "sb_reset_launch_count": (None, []),
     "sb_debug_word": (c_uint, []),
     "sb_tune": (c_int, [c_int, c_int]),
+    "sb_host_alloc": (c_void_p, [c_size_t, c_int]),
+    "sb_host_free": (c_int, [c_void_p]),
     "sb_corr_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "sb_corr": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_feat_to_tokens_bf16": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
@@ -122,3 +124,31 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     load().sb_reset_launch_count()
+
+
+class _HostBuffer:
+    """Owner of one cudaHostAlloc'd block (freed when the last tensor viewing it dies)."""
+
+    def __init__(self, nbytes: int, write_combined: bool):
+        self.ptr = load().sb_host_alloc(nbytes, 1 if write_combined else 0)
+        if not self.ptr:
+            raise RuntimeError(f"sb_host_alloc({nbytes}): {last_error()}")
+        self.nbytes = nbytes
+        self.buf = (ctypes.c_char * nbytes).from_address(self.ptr)
+
+    def __del__(self):
+        try:
+            load().sb_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_like(t: torch.Tensor, write_combined: bool = False) -> torch.Tensor:
+    """A page-locked host tensor with ``t``'s shape / dtype holding a copy of ``t`` (CPU tensor)."""
+    src = t.contiguous()
+    nbytes = max(src.numel() * src.element_size(), 1)
+    owner = _HostBuffer(nbytes, write_combined)
+    out = torch.frombuffer(owner.buf, dtype=src.dtype, count=src.numel()).view(src.shape)
+    out._sb_owner = owner           # keeps the allocation alive as long as the tensor object
+    out.copy_(src)
+    return out

@@ -91,6 +91,27 @@ int sb_tune(int key, int value) {
   sb::g_tune[key].store(value, std::memory_order_relaxed);
   return SB_OK;
 }
+// Pinned host staging buffers for the host-resident data path (pipeline.StreamedHotPath).
+// write_combined != 0: cudaHostAllocWriteCombined — not snooped by the CPU caches, faster for the
+// device to read over PCIe; meant for buffers the CPU only ever fills sequentially.
+void* sb_host_alloc(size_t bytes, int write_combined) {
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0));
+  if (e != cudaSuccess) {
+    sb::set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+int sb_host_free(void* p) {
+  if (!p) return SB_OK;
+  cudaError_t e = cudaFreeHost(p);
+  if (e != cudaSuccess) {
+    sb::set_error("cudaFreeHost failed: %s", cudaGetErrorString(e));
+    return SB_ECUDA;
+  }
+  return SB_OK;
+}
 void sb_reset_launch_count(void) { sb::g_launches.store(0, std::memory_order_relaxed); }
 
 }  // extern "C"

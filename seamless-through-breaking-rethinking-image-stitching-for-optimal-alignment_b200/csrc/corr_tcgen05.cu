@@ -110,6 +110,7 @@ struct CorrParams {
   int H2h, H2q, H2e;            // H2/2, H2/4, H2/8 (pooling)
   float* lvl1; float* lvl2; float* lvl3;
   unsigned int* dbg;
+  int store_policy;             // L2 policy of the output stores (sb_tune SB_TUNE_CORR_STORE_POLICY)
 };
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
@@ -281,6 +282,14 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t my_stage = sStage + wq * kSBufs * kStageBufBytes;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
     uint32_t acc = 0, acc_par = 0, sbuf = 0;
+    // experiment knob: L2 policy of the output stores (0 none, 1 evict_first, 2 evict_last)
+    const uint64_t st_policy = p.store_policy == 1 ? ptx::l2_policy_evict_first()
+                               : (p.store_policy == 2 ? ptx::l2_policy_evict_last() : 0ull);
+#define TMA_STORE_V(map_, smem_, c0_, c1_, c2_)                                             \
+  do {                                                                                      \
+    if (p.store_policy) ptx::tma_store_3d_hint(map_, smem_, c0_, c1_, c2_, st_policy);      \
+    else ptx::tma_store_3d(map_, smem_, c0_, c1_, c2_);                                     \
+  } while (0)
     // pooling state (one query row per thread)
     float h1[32];   // level-1 partial sums of the current tile (target row pair)
     float h2[16];   // level-2 partial sums across tile pairs
@@ -314,7 +323,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_store_3d(map, my_stage + sbuf * kStageBufBytes, c0, r0, b);
+            TMA_STORE_V(map, my_stage + sbuf * kStageBufBytes, c0, r0, b);
             ptx::tma_store_commit();
           }
           if (++sbuf == kSBufs) sbuf = 0;
@@ -431,7 +440,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              ptx::tma_store_3d(&map_v, my_stage + sbuf * kStageBufBytes, t * BN + s2 * 64, mb * BM + wq * 32, b);
+              TMA_STORE_V(&map_v, my_stage + sbuf * kStageBufBytes, t * BN + s2 * 64, mb * BM + wq * 32, b);
               ptx::tma_store_commit();
             }
             if (++sbuf == kSBufs) sbuf = 0;
@@ -471,7 +480,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_store_3d(&map_v, my_stage + sbuf * kStageBufBytes, t * BN + sl * 32,
+            TMA_STORE_V(&map_v, my_stage + sbuf * kStageBufBytes, t * BN + sl * 32,
                               mb * BM + wq * 32, b);
             ptx::tma_store_commit();
           }
@@ -514,7 +523,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                  ptx::tma_store_3d(&map_l1, my_stage + sbuf * kStageBufBytes, tcol * 32, mb * BM + wq * 32, b);
+                  TMA_STORE_V(&map_l1, my_stage + sbuf * kStageBufBytes, tcol * 32, mb * BM + wq * 32, b);
                   ptx::tma_store_commit();
                 }
                 if (++sbuf == kSBufs) sbuf = 0;
@@ -552,7 +561,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                  ptx::tma_store_3d(&map_l2, my_stage + sbuf * kStageBufBytes, (t >> 2) * 32, mb * BM + wq * 32, b);
+                  TMA_STORE_V(&map_l2, my_stage + sbuf * kStageBufBytes, (t >> 2) * 32, mb * BM + wq * 32, b);
                   ptx::tma_store_commit();
                 }
                 if (++sbuf == kSBufs) sbuf = 0;
@@ -772,6 +781,8 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   p.lvl2 = fused_pool ? lvl2 : nullptr;
   p.lvl3 = fused_pool ? lvl3 : nullptr;
   p.dbg = g_dbg;
+  p.store_policy = tune_get(SB_TUNE_CORR_STORE_POLICY, 1) & 3;   // default evict_first (3 = no hint)
+  if (p.store_policy == 3) p.store_policy = 0;
 
   const int grid = (int)((p.n_units < kNumSMs) ? p.n_units : kNumSMs);
   static bool attr_set = false;

@@ -203,6 +203,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ================================================================ producer
     if (lane == 0) {
       uint32_t a_par = 0, stage = 0, b_par = 0;
+      // experiment knob (store_policy bit 2): operand loads keep their lines in L2 (evict_last)
+      const uint64_t ld_policy = (p.store_policy & 4) ? ptx::l2_policy_evict_last() : 0ull;
       // TWO_CTA: completions of both CTAs' loads are counted on the LEADER's "full" barriers
       const uint32_t a_full_tgt = TWO_CTA ? ptx::mapa_shared(bar_a_full, 0) : bar_a_full;
       for (long long u = unit0; u < p.n_units; u += unit_step) {
@@ -215,6 +217,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         else if (leader) ptx::mbar_arrive_expect_tx(bar_a_full, 2 * panel_tx);
         for (int kp = 0; kp < p.KP; ++kp) {
           if (TWO_CTA) ptx::tma_load_3d_2cta(sA + kp * kPanelBytes, &map_a, a_full_tgt, kp * BKP, mb * BM, b);
+          else if (ld_policy) ptx::tma_load_3d_hint(sA + kp * kPanelBytes, &map_a, bar_a_full, kp * BKP, mb * BM, b, ld_policy);
           else ptx::tma_load_3d(sA + kp * kPanelBytes, &map_a, bar_a_full, kp * BKP, mb * BM, b);
         }
         a_par ^= 1;
@@ -228,6 +231,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int kp = 0; kp < p.KP; ++kp) {
             const uint32_t dstb = sB + (stage * kMaxPanels + kp) * kBPanelBytes;
             if (TWO_CTA) ptx::tma_load_3d_2cta(dstb, &map_b, b_full_tgt, kp * BKP, t * BN + (int)cta_rank * kBRows, b);
+            else if (ld_policy) ptx::tma_load_3d_hint(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, b, ld_policy);
             else ptx::tma_load_3d(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, b);
           }
           if (++stage == kStages) { stage = 0; b_par ^= 1; }
@@ -283,11 +287,11 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
     uint32_t acc = 0, acc_par = 0, sbuf = 0;
     // experiment knob: L2 policy of the output stores (0 none, 1 evict_first, 2 evict_last)
-    const uint64_t st_policy = p.store_policy == 1 ? ptx::l2_policy_evict_first()
-                               : (p.store_policy == 2 ? ptx::l2_policy_evict_last() : 0ull);
+    const uint64_t st_policy = (p.store_policy & 3) == 1 ? ptx::l2_policy_evict_first()
+                               : ((p.store_policy & 3) == 2 ? ptx::l2_policy_evict_last() : 0ull);
 #define TMA_STORE_V(map_, smem_, c0_, c1_, c2_)                                             \
   do {                                                                                      \
-    if (p.store_policy) ptx::tma_store_3d_hint(map_, smem_, c0_, c1_, c2_, st_policy);      \
+    if (p.store_policy & 3) ptx::tma_store_3d_hint(map_, smem_, c0_, c1_, c2_, st_policy);  \
     else ptx::tma_store_3d(map_, smem_, c0_, c1_, c2_);                                     \
   } while (0)
     // pooling state (one query row per thread)
@@ -781,8 +785,10 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   p.lvl2 = fused_pool ? lvl2 : nullptr;
   p.lvl3 = fused_pool ? lvl3 : nullptr;
   p.dbg = g_dbg;
-  p.store_policy = tune_get(SB_TUNE_CORR_STORE_POLICY, 1) & 3;   // default evict_first (3 = no hint)
-  if (p.store_policy == 3) p.store_policy = 0;
+  {
+    const int tp = tune_get(SB_TUNE_CORR_STORE_POLICY, 1);   // bits 0-1: stores (1 evict_first default, 2 evict_last, 3 none); bit 2: operand loads evict_last
+    p.store_policy = ((tp & 3) == 3 ? 0 : (tp & 3)) | (tp & 4);
+  }
 
   const int grid = (int)((p.n_units < kNumSMs) ? p.n_units : kNumSMs);
   static bool attr_set = false;

@@ -11,7 +11,7 @@ B = 16
 f1 = torch.randn(B, 256, 64, 64, device="cuda", generator=g); f2 = torch.randn(B, 256, 64, 64, device="cuda", generator=g)
 t1, t2 = C.tokens_bf16(f1), C.tokens_bf16(f2)
 ref = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_levels=3)
-for pol in (3, 1, 2):
+for pol in (3, 1, 5):
     lib.sb_tune(7, pol)
     out = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_levels=3)
     same = torch.equal(out[0], ref[0]) and all(torch.equal(a, b) for a, b in zip(out[1], ref[1]))

@@ -185,6 +185,7 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // ================================================================ producer
     if (lane == 0) {
       uint32_t stage = 0, par = 0;
+      const uint64_t pol_keep = ptx::l2_policy_evict_last(), pol_stream = ptx::l2_policy_evict_first();
       for (long long u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const int nt = (int)(u % p.NT);
         const long long u2 = u / p.NT;
@@ -193,10 +194,13 @@ attn_v_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           ptx::mbar_wait(bar_empty + 8 * stage, par ^ 1, 0x21, p.dbg);
           ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);   // rows past Nq / keys past Nk arrive as zeros
           const uint32_t sa = smem_base + stage * kStageBytes;
-          ptx::tma_load_3d(sa + MBLK * kGBlkBytes, &map_b, bar_full + 8 * stage, ks * kKStep, nt * GN, bh);
+          // B (v / the second operand) is re-read by every unit of its batch element: keep it in L2;
+          // A (the attention matrix) streams through once: evict first
+          ptx::tma_load_3d_hint(sa + MBLK * kGBlkBytes, &map_b, bar_full + 8 * stage, ks * kKStep, nt * GN, bh, pol_keep);
 #pragma unroll
           for (int m = 0; m < MBLK; ++m)
-            ptx::tma_load_3d(sa + m * kGBlkBytes, &map_a, bar_full + 8 * stage, ks * kKStep, (mu * MBLK + m) * GM, bh);
+            ptx::tma_load_3d_hint(sa + m * kGBlkBytes, &map_a, bar_full + 8 * stage, ks * kKStep, (mu * MBLK + m) * GM, bh,
+                                  p.row_major ? pol_keep : pol_stream);
           if (++stage == kStages) { stage = 0; par ^= 1; }
         }
       }

@@ -126,8 +126,12 @@ def reset_launch_count() -> None:
     load().sb_reset_launch_count()
 
 
+_HOST_BUFFERS = []   # owners of cudaHostAlloc'd blocks; views of a block may outlive the tensor that
+                     # pinned_like() returned, so blocks are only released by free_pinned_buffers()
+
+
 class _HostBuffer:
-    """Owner of one cudaHostAlloc'd block (freed when the last tensor viewing it dies)."""
+    """Owner of one cudaHostAlloc'd block."""
 
     def __init__(self, nbytes: int, write_combined: bool):
         self.ptr = load().sb_host_alloc(nbytes, 1 if write_combined else 0)
@@ -136,11 +140,10 @@ class _HostBuffer:
         self.nbytes = nbytes
         self.buf = (ctypes.c_char * nbytes).from_address(self.ptr)
 
-    def __del__(self):
-        try:
+    def free(self):
+        if self.ptr:
             load().sb_host_free(self.ptr)
-        except Exception:
-            pass
+            self.ptr = None
 
 
 def pinned_like(t: torch.Tensor, write_combined: bool = False) -> torch.Tensor:
@@ -148,7 +151,13 @@ def pinned_like(t: torch.Tensor, write_combined: bool = False) -> torch.Tensor:
     src = t.contiguous()
     nbytes = max(src.numel() * src.element_size(), 1)
     owner = _HostBuffer(nbytes, write_combined)
+    _HOST_BUFFERS.append(owner)
     out = torch.frombuffer(owner.buf, dtype=src.dtype, count=src.numel()).view(src.shape)
-    out._sb_owner = owner           # keeps the allocation alive as long as the tensor object
     out.copy_(src)
     return out
+
+
+def free_pinned_buffers() -> None:
+    """Release every block handed out by pinned_like(); the caller guarantees no tensor uses them any more."""
+    while _HOST_BUFFERS:
+        _HOST_BUFFERS.pop().free()

@@ -108,3 +108,16 @@ def test_patch_reference_assigns_call_sites():
             if k not in saved and (k.startswith("core") or k.startswith("timm") or k.startswith("skimage")):
                 del sys.modules[k]
         sys.path[:] = saved_path
+
+
+def test_header_is_plain_c():
+    """include/stitch_b200.h is the drop-in boundary: it must compile as C99 and as C++17 on its own."""
+    import subprocess
+    import tempfile
+    src = '#include "stitch_b200.h"\nint main(void) { return sb_version() > 0 ? 0 : 1; }\n'
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "hdr.c")
+        open(path, "w").write(src)
+        inc = os.path.join(ROOT, "include")
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, path], check=True)
+        subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", inc, path], check=True)

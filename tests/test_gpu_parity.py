@@ -512,6 +512,26 @@ def test_ccl_golden_and_full_size(sb):
         assert max_abs(got, ref) <= tol, (scale, max_abs(got, ref))
 
 
+def test_next_rows_empty_and_bad_inputs(sb):
+    """Empty batches return empty results of the reference's shape; wrong devices / shapes raise."""
+    z = lambda *sh: torch.zeros(*sh, device="cuda")
+    assert tuple(sb.decoder.upsample_flow(z(0, 2, 8, 8), z(0, 576, 8, 8)).shape) == (0, 2, 64, 64)
+    assert tuple(sb.udis2_homography.CCL(z(0, 64, 8, 8), z(0, 64, 8, 8)).shape) == (0, 2, 8, 8)
+    assert tuple(sb.kornia_tps.warp_image_tps(z(0, 6, 8, 8), z(0, 4, 2), z(0, 4, 2), z(0, 3, 2)).shape) == (0, 6, 8, 8)
+    assert tuple(sb.kornia_tps.grid_sample(z(0, 3, 8, 8), z(0, 5, 7, 2)).shape) == (0, 3, 5, 7)
+    assert tuple(sb.gma.attn_matmul_v(z(0, 64, 64), z(0, 128, 64)).shape) == (0, 128, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sb.decoder.upsample_flow(torch.zeros(1, 2, 8, 8), torch.zeros(1, 576, 8, 8))
+    with pytest.raises(ValueError):
+        sb.decoder.upsample_flow(z(1, 2, 8, 8), z(1, 64, 8, 8))
+    with pytest.raises(ValueError):
+        sb.udis2_homography.CCL(z(1, 64, 8, 8), z(1, 64, 8, 9))
+    with pytest.raises(RuntimeError, match="dim_head"):
+        sb.gma.attn_matmul_v(z(1, 64, 64), z(1, 96, 64))
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        sb.gma.attn_matmul_v(z(1, 66, 66), z(1, 128, 66))
+
+
 # ===================================================================== N2 (next row 2)
 def test_upsample_flow_golden(sb):
     c = cases.upsample_small()

@@ -252,7 +252,8 @@ int sb_gemm_nt_tf32(const float* A, const float* B, float* D, int BH, int M, int
  * Replaces UDIS2Network.CCL(feature_1, feature_2)  (core/UDIS2/Homography/network.py:147-199):
  * L2-normalise over channels, 3x3-patch all-pairs correlation, softmax(10 x) over the patches,
  * expected displacement. feature_1/2 [B,C,H,W] -> flow [B,2,H,W] (channel 0 = w, 1 = h).
- * workspace: caller-provided, 256-byte aligned, >= sb_ccl_workspace_bytes(). H*W <= 4096, C % 4 == 0. */
+ * workspace: caller-provided, 256-byte aligned, >= sb_ccl_workspace_bytes(). C % 4 == 0; H*W unbounded when H*W % 4 == 0 and
+ * W <= 256 (the staged kernel), else H*W <= 4096 (the row-streaming fallback). */
 size_t sb_ccl_workspace_bytes(int B, int C, int H, int W);
 int sb_ccl(const float* feature_1, const float* feature_2, float* flow, void* workspace,
            size_t workspace_bytes, int B, int C, int H, int W, float softmax_scale, sb_stream_t stream);

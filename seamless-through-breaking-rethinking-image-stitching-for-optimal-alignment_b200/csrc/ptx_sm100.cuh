@@ -70,6 +70,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap,
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// 1-D bulk copy global -> shared (no tensor map): size and both addresses multiples of 16 bytes
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+      : "memory");
+}
 // same, with an L2 cache-policy operand (createpolicy)
 __device__ __forceinline__ void tma_load_3d_hint(uint32_t smem_dst, const void* tmap, uint32_t bar,
                                                  int c0, int c1, int c2, uint64_t policy) {

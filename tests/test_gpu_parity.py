@@ -549,6 +549,19 @@ def test_ccl_golden_and_full_size(sb):
         assert max_abs(got, ref) <= tol, (scale, max_abs(got, ref))
 
 
+@pytest.mark.parametrize("h,w", [(9, 7), (6, 10), (36, 40)])
+def test_ccl_shapes(sb, h, w):
+    """H*W % 4 != 0 (row-streaming fallback kernel), W % 4 != 0 (a CTA's positions wrap image rows) and
+    H*W > 1024 (the staged kernel walks q in chunks with a running softmax)."""
+    gen = torch.Generator().manual_seed(83 + h)
+    f1 = torch.relu(torch.randn(2, 64, h, w, generator=gen))
+    f2 = torch.roll(f1, shifts=(1, -2), dims=(2, 3)) + 0.3 * torch.relu(torch.randn(2, 64, h, w, generator=gen))
+    got = host(sb.udis2_homography.CCL(cu(f1), cu(f2)))
+    ref = so.ccl(f1.numpy(), f2.numpy())
+    assert got.shape == ref.shape == (2, 2, h, w)
+    assert max_abs(got, ref) <= 1e-2 * max(1.0, max(h, w) / 12.0), max_abs(got, ref)
+
+
 def test_next_rows_empty_and_bad_inputs(sb):
     """Empty batches return empty results of the reference's shape; wrong devices / shapes raise."""
     z = lambda *sh: torch.zeros(*sh, device="cuda")

@@ -222,6 +222,14 @@ int sb_tps_kornia_warp(const float* image, const float* centers, const float* kw
 int sb_grid_sample(const float* img, const float* grid, float* out, int N, int C, int H, int W,
                    int Ho, int Wo, int align_corners, sb_stream_t stream);
 
+/* Attention.forward in two passes over the same tcgen05 contraction (core/FlowFormer/PerCostFormer3/gma.py:54-76):
+ * attn[b, i, :] = tf32(softmax_j(tok_q[b, i, :] . tok_k[b, j, :])) without a round trip of the fp32 logits
+ * through HBM: pass 1 keeps the running (max, sum of exp) of every query row, pass 2 recomputes the
+ * contraction and writes normalised probabilities.  tok_q / tok_k: bf16 token-major maps from
+ * sb_feat_to_tokens_bf16 ([B, N, Cpad], scale folded into q); attn [B, Nq, Nk] fp32 (Nk % 4 == 0);
+ * stats: workspace of B * Nq * 2 floats (8-byte aligned). */
+int sb_attn_softmax_tokens(const void* tok_q, const void* tok_k, float* attn, float* stats, int B, int C,
+                           int Nq, int Nk, sb_stream_t stream);
 /* ------------------------------------------------------------------ N1 ("next" row 1)
  * GMA attention / aggregation (core/FlowFormer/PerCostFormer3/gma.py:54-76, :102-115).
  *   sb_softmax_rows: in-place softmax over rows of a dense fp32 matrix (the `sim.softmax(dim=-1)`

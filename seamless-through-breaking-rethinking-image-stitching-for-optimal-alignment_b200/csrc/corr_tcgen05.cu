@@ -111,6 +111,8 @@ struct CorrParams {
   float* lvl1; float* lvl2; float* lvl3;
   unsigned int* dbg;
   int store_policy;             // L2 policy of the output stores (sb_tune SB_TUNE_CORR_STORE_POLICY)
+  int tpu;                      // tiles per unit (kTilesPerUnit; 8 for POOL == 2; NT for the softmax statistics pass)
+  float* smx;                   // SMX: per-row (max, sum of exp) [B, N1, 2]; written by pass 1, read by pass 2
 };
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
@@ -133,8 +135,23 @@ constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN
 // 2 = fused pyramid for W2 == 128 (a tile is ONE target row: the epilogue drains tile PAIRS, reading
 // both rows' accumulators from TMEM slice by slice, so level 1 needs no cross-tile carry; units are
 // 8 tiles = 8 target rows so that level 3 closes inside the unit).
-template <int POOL, bool BF16OUT = false, bool TWO_CTA = false>
-__global__ void __launch_bounds__(256, 1)
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, 2 ulp; -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// SMX (never with POOL / BF16OUT / TWO_CTA): row softmax of the volume fused as two passes over the SAME
+// contraction instead of a round trip of the fp32 logits through HBM (GMA Attention.forward):
+//   1 = statistics: a unit is a whole row block (all NT tiles); every epilogue thread keeps the running
+//       maximum and sum of exp of its query row and writes (max, sum) at the end — nothing else is stored;
+//       launched with TWO epilogue warp quads (384 threads) that take alternate tiles, because one warp per
+//       SM sub-partition cannot hide the TMEM-load and ex2 latencies on its own; their partial (max, sum)
+//       are merged through shared memory;
+//   2 = normalise: the contraction is recomputed and every value leaves as
+//       tf32(exp(x - max) / sum) through the usual staged TMA stores.
+template <int POOL, bool BF16OUT = false, bool TWO_CTA = false, int SMX = 0>
+__global__ void __launch_bounds__(SMX == 1 ? 384 : 256, 1)
 corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_l1,
                  const __grid_constant__ CUtensorMap map_l2, const CorrParams p) {
@@ -163,7 +180,6 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // work is enumerated per cluster in TWO_CTA mode
   const long long unit0 = TWO_CTA ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
   const long long unit_step = TWO_CTA ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
-  constexpr int kTPU = (POOL == 2) ? 8 : kTilesPerUnit;          // tiles per unit
   constexpr int kBRows = TWO_CTA ? BN / 2 : BN;                   // B rows this CTA loads per tile
   constexpr int kBPanelBytes = kBRows * 128;
 
@@ -221,8 +237,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           else ptx::tma_load_3d(sA + kp * kPanelBytes, &map_a, bar_a_full, kp * BKP, mb * BM, b);
         }
         a_par ^= 1;
-        const int t0 = ng * kTPU;
-        const int t1 = min(t0 + kTPU, p.NT);
+        const int t0 = ng * p.tpu;
+        const int t1 = min(t0 + p.tpu, p.NT);
         for (int t = t0; t < t1; ++t) {
           ptx::mbar_wait(bar_b_empty + 8 * stage, b_par ^ 1, 2, p.dbg);
           if (!TWO_CTA) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, b_tx);
@@ -245,8 +261,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t a_par = 0, stage = 0, b_par = 0, acc = 0, acc_par = 0;
       for (long long u = unit0; u < p.n_units; u += unit_step) {
         const int ng = (int)(u % p.NG);
-        const int t0 = ng * kTPU;
-        const int t1 = min(t0 + kTPU, p.NT);
+        const int t0 = ng * p.tpu;
+        const int t1 = min(t0 + p.tpu, p.NT);
         ptx::mbar_wait(bar_a_full, a_par, 3, p.dbg);
         a_par ^= 1;
         for (int t = t0; t < t1; ++t) {
@@ -282,7 +298,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncwarp();
   } else if (warp >= 4) {
     // ================================================================ epilogue
-    const int wq = warp - 4;                       // TMEM lane quarter == warp % 4
+    const int wq = (warp - 4) & 3;                 // TMEM lane quarter == warp % 4
+    const int quad = (warp - 4) >> 2;              // second epilogue quad: SMX == 1 only
     const uint32_t my_stage = sStage + wq * kSBufs * kStageBufBytes;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
     uint32_t acc = 0, acc_par = 0, sbuf = 0;
@@ -305,11 +322,77 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const long long r1 = u / p.NG;
       const int mb = (int)(r1 % p.MB) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
       const int b = (int)(r1 / p.MB);
-      const int t0 = ng * kTPU;
-      const int t1 = min(t0 + kTPU, p.NT);
+      const int t0 = ng * p.tpu;
+      const int t1 = min(t0 + p.tpu, p.NT);
       const int row = mb * BM + wq * 32 + lane;    // query index within the batch
       const bool row_ok = row < p.N1;
       const long long q = (long long)b * p.N1 + row;
+      constexpr float kLog2e = 1.4426950408889634f;
+      if (SMX == 1) {
+        // ------------------------------------------------ softmax statistics of this thread's query row
+        float m = -INFINITY, l = 0.0f;
+        for (int t = t0; t < t1; ++t) {
+          if ((int)(acc & 1u) != quad) {               // the other quad's tile
+            if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
+            continue;
+          }
+          ptx::mbar_wait(bar_t_full + 8 * acc, acc_par, 6, p.dbg);
+          ptx::tc_fence_after_sync();
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(lane_taddr + acc * BN + sl * 32, r);
+            ptx::tmem_ld_wait();
+            const int cbase = t * BN + sl * 32;
+            if (cbase >= p.N2) continue;               // columns past the last key: zero-filled operands, not logits
+            // four independent chains for the maximum and the sum: one warp per SM sub-partition drains
+            // the tile, so a 32-long dependent chain would be pure latency
+            float x[32];
+            if (cbase + 32 <= p.N2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = (cbase + j < p.N2) ? __uint_as_float(r[j]) : -INFINITY;
+            }
+            float c4[4] = {x[0], x[1], x[2], x[3]};
+#pragma unroll
+            for (int j = 4; j < 32; ++j) c4[j & 3] = fmaxf(c4[j & 3], x[j]);
+            const float cm = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
+            if (cm > m) {                              // exp2(-inf) = 0 covers the first slice
+              l *= ex2_approx((m - cm) * kLog2e);
+              m = cm;
+            }
+            const float mb2 = m * kLog2e;
+            float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s4[j & 3] += ex2_approx(__fmaf_rn(x[j], kLog2e, -mb2));
+            const float sacc = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            l += sacc;
+          }
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_t_empty + 8 * acc);
+          if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
+        }
+        // merge the two quads' partial statistics of the same 128 rows (staging area is unused in this mode)
+        float2* s_ml = reinterpret_cast<float2*>(smem_gen + kSmemA + kSmemB) + wq * 32 + lane;
+        if (quad == 1) *s_ml = make_float2(m, l);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (quad == 0) {
+          const float2 o = *s_ml;                      // (-inf, 0) when the other quad had no tile
+          const float mm = fmaxf(m, o.x);
+          l = l * ex2_approx((m - mm) * kLog2e) + o.y * ex2_approx((o.x - mm) * kLog2e);
+          if (row_ok) *reinterpret_cast<float2*>(p.smx + 2 * q) = make_float2(mm, l);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // s_ml is free for the next unit
+        continue;
+      }
+      float smx_mb2 = 0.0f;                       // max * log2(e) + log2(sum): exp(x - max) / sum = 2^(x log2(e) - smx_mb2)
+      if (SMX == 2 && row_ok) {
+        const float2 ml = *reinterpret_cast<const float2*>(p.smx + 2 * q);
+        smx_mb2 = __fmaf_rn(ml.x, kLog2e, log2f(ml.y));
+      }
       if (POOL == 2) {
         // ---------------------------------------------------------- W2 == 128: tile pairs
         // staged 32 x 128-byte block -> one TMA store (volume slice, level-1 half row, level-2 row)
@@ -455,6 +538,15 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(lane_taddr + acc * BN + sl * 32, r);
           ptx::tmem_ld_wait();
+          if (SMX == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float pr = ex2_approx(__fmaf_rn(__uint_as_float(r[j]), kLog2e, -smx_mb2));
+              // cvt.rna.tf32 (round to nearest, ties away) of a non-negative finite value with integer
+              // ops: the conversion instruction shares the 16-lane unit with ex2
+              r[j] = (__float_as_uint(pr) + 0x1000u) & 0xffffe000u;
+            }
+          }
           if (POOL == 1) {
             // W2 == 64: slices 0,1 = target row 2t (w 0..31, 32..63); 2,3 = row 2t+1.
             // avg_pool2d order: ((a00 + a01) + a10) + a11, then * 0.25
@@ -688,13 +780,22 @@ extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, fl
 namespace sb {
 static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, long long vol_pitch, bool bf16_out,
                             float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1, int H2, int W2,
-                            sb_stream_t stream);
+                            sb_stream_t stream, float* smx_stats = nullptr);
 }
 
 extern "C" int sb_corr_tokens_pitched(const void* tok1, const void* tok2, float* vol, long long vol_pitch,
                                       float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1,
                                       int H2, int W2, sb_stream_t stream) {
   return sb::corr_tokens_impl(tok1, tok2, vol, vol_pitch, false, lvl1, lvl2, lvl3, B, C, H1, W1, H2, W2, stream);
+}
+
+// softmax over the keys of q . k^T, TF32-rounded probabilities [B, Nq, Nk] (GMA Attention.forward);
+// stats: workspace of B * Nq * 2 floats.
+extern "C" int sb_attn_softmax_tokens(const void* tok_q, const void* tok_k, float* attn, float* stats, int B, int C,
+                                      int Nq, int Nk, sb_stream_t stream) {
+  if (!stats) { sb::set_error("sb_attn_softmax_tokens: null stats workspace"); return SB_EINVAL; }
+  return sb::corr_tokens_impl(tok_q, tok_k, attn, (long long)Nk, false, nullptr, nullptr, nullptr, B, C, 1, Nq, 1, Nk,
+                              stream, stats);
 }
 
 // bf16 volume [B, N1, N2] (N2 % 8 == 0): opt-in, not the reference's dtype
@@ -707,7 +808,7 @@ extern "C" int sb_corr_tokens_bf16out(const void* tok1, const void* tok2, void* 
 namespace sb {
 static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, long long vol_pitch, bool bf16_out,
                             float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1, int H2, int W2,
-                            sb_stream_t stream) {
+                            sb_stream_t stream, float* smx_stats) {
   float* vol = static_cast<float*>(vol_any);
   SB_ENTER();
   SB_REQUIRE(tok1 && tok2 && vol, SB_EINVAL, "sb_corr_tokens: null pointer");
@@ -739,8 +840,10 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   rc = make_map_3d(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok1, Cpad, N1, B, BKP, BM, "A");
   if (rc) return rc;
   // CTA-pair mode (tcgen05 cta_group::2): every CTA loads half of each B tile
-  const bool two_cta = tune_get(SB_TUNE_CORR_2CTA, 1) == 2 && !(lvl1 || lvl2 || lvl3) ? true
-                       : (tune_get(SB_TUNE_CORR_2CTA, 1) == 2 && W2 == 64);   // the W2 == 128 pyramid runs one CTA per tile
+  SB_REQUIRE(!smx_stats || (!bf16_out && !want_pool), SB_EINVAL, "sb_attn_softmax_tokens: fp32 output without pyramid only");
+  SB_REQUIRE(!smx_stats || (reinterpret_cast<uintptr_t>(smx_stats) & 7) == 0, SB_EINVAL, "sb_attn_softmax_tokens: stats must be 8-byte aligned");
+  const bool two_cta = smx_stats ? false : (tune_get(SB_TUNE_CORR_2CTA, 1) == 2 && !(lvl1 || lvl2 || lvl3) ? true
+                       : (tune_get(SB_TUNE_CORR_2CTA, 1) == 2 && W2 == 64));   // the W2 == 128 pyramid runs one CTA per tile
   rc = make_map_3d(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, tok2, Cpad, N2, B, BKP, two_cta ? BN / 2 : BN, "B");
   if (rc) return rc;
   if (bf16_out)
@@ -778,6 +881,8 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   if (two_cta) p.MB = (p.MB + 1) / 2;             // units are pairs of query blocks
   p.NT = (int)((N2 + BN - 1) / BN);
   const int tpu = (pool_mode == 2) ? 8 : kTilesPerUnit;
+  p.tpu = tpu;
+  p.smx = smx_stats;
   p.NG = (p.NT + tpu - 1) / tpu;
   p.n_units = (long long)B * p.MB * p.NG;
   p.H2h = H2 / 2; p.H2q = H2 / 4; p.H2e = H2 / 8;
@@ -800,7 +905,20 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     attr_set = true;
+  }
+  if (smx_stats) {
+    // pass 1: one unit per row block, all NT tiles; pass 2: the usual units
+    CorrParams p1 = p;
+    p1.tpu = p.NT; p1.NG = 1; p1.n_units = (long long)B * p.MB;
+    const int grid1 = (int)((p1.n_units < kNumSMs) ? p1.n_units : kNumSMs);
+    corr_umma_kernel<0, false, false, 1><<<grid1, 384, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p1);
+    SB_LAUNCH_CHECK("corr_umma_kernel<softmax statistics>");
+    corr_umma_kernel<0, false, false, 2><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
+    SB_LAUNCH_CHECK("corr_umma_kernel<softmax normalise>");
+    return SB_OK;
   }
   if (two_cta) {
     long long clusters = p.n_units < kNumSMs / 2 ? p.n_units : kNumSMs / 2;

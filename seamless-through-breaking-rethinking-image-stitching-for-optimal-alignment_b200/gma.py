@@ -63,6 +63,16 @@ def attention(fmap, to_qk_weight, heads: int = 1, scale: float | None = None, dt
         return out.view(b, heads, n, n)
     if dtype != torch.float32:
         raise ValueError("attention: dtype must be torch.float32 or torch.bfloat16")
+    if n % 4 == 0:
+        # two passes over the same bf16 x bf16 -> fp32 contraction (row statistics, then normalised
+        # probabilities): the fp32 logits never travel through HBM
+        lib = _lib.load()
+        tq, tk = corr_mod.tokens_bf16(q), corr_mod.tokens_bf16(k)
+        attn = torch.empty((b * heads, n, n), dtype=torch.float32, device=tq.device)
+        stats = torch.empty((b * heads, n, 2), dtype=torch.float32, device=tq.device)
+        _lib.check(lib.sb_attn_softmax_tokens(_lib.ptr(tq), _lib.ptr(tk), _lib.ptr(attn), _lib.ptr(stats), b * heads,
+                                              q.shape[1], n, n, _lib.stream_ptr()), "sb_attn_softmax_tokens")
+        return attn.view(b, heads, n, n)
     sim = corr_mod.corr(q, k).view(b * heads, n, n)          # bf16 x bf16 -> fp32 on the tensor cores
     softmax_rows_(sim, to_tf32=True)
     return sim.view(b, heads, n, n)

@@ -471,6 +471,27 @@ def test_gma_golden(sb):
     assert max_abs(o2, out) == 0.0
 
 
+@pytest.mark.parametrize("h,w", [(12, 16), (30, 46), (6, 6), (64, 64)])
+def test_gma_attention_two_pass_vs_unfused(sb, h, w):
+    """The fused two-pass softmax (statistics pass + normalising pass over the same tcgen05 contraction)
+    against the unfused path (fp32 logits -> sb_softmax_rows) on the same projections: token counts that
+    are / are not multiples of the 128-wide tiles; rows sum to 1; probabilities are TF32 values."""
+    gen = torch.Generator(device="cuda").manual_seed(72 + h)
+    fmap = torch.randn(2, 128, h, w, device="cuda", generator=gen)
+    w_qk = (torch.rand(256, 128, 1, 1, device="cuda", generator=gen) * 2 - 1) * 0.25
+    n = h * w
+    attn = sb.gma.attention(fmap, w_qk).view(2, n, n)
+    q, k = sb.gma.project_qk(fmap, w_qk)
+    sim = sb.corr.corr(q, k).view(2, n, n)
+    ref64 = torch.softmax(sim.double(), dim=-1)
+    unf = sb.gma.softmax_rows_(sim.clone(), to_tf32=True)
+    assert float((attn.sum(-1) - 1).abs().max()) <= 2e-3
+    # same logits on both sides: differences are ex2.approx vs expf (~2 ulp) and TF32 rounding flips (2^-11)
+    assert float(((attn - unf).abs() / (unf + 1e-6)).max()) <= 2e-3
+    assert float(((attn.double() - ref64).abs() / (ref64 + 1e-6)).max()) <= 1e-3
+    assert int((attn.view(torch.int32) & 0x1fff).count_nonzero()) == 0          # low 13 mantissa bits clear
+
+
 def test_gma_bf16_attention_option(sb):
     """Opt-in bf16 probabilities: aggregate within 1e-2 * scale of the fp32 reference, and the kernel
     within 1e-3 * scale of fp64 on its own bf16 operands."""

@@ -88,6 +88,16 @@ def main():
         sim.copy_(attn)
         sb.gma.softmax_rows_(sim)
     report("gma softmax_rows (in place)", timeit(_softmax_of_copy, n=5) - timeit(lambda: sim.copy_(attn), n=5), B * n * n * 8)
+    qq, kk = sb.gma.project_qk(fm, w_qk)
+    tq, tk = sb.corr.tokens_bf16(qq), sb.corr.tokens_bf16(kk)
+    stats = torch.empty(B, n, 2, device="cuda")
+    lib = sb._lib.load()
+    P = sb._lib.ptr
+    def _fused():
+        sb._lib.check(lib.sb_attn_softmax_tokens(P(tq), P(tk), P(sim), P(stats), B, 128, n, n, sb._lib.stream_ptr()), "attn")
+    ms = timeit(_fused, n=5)
+    report("gma attention, fused 2-pass softmax", ms, B * n * n * 4)
+    print(f"{'':34s} (unfused: q.k^T volume + softmax_rows = the two lines above; 2 x {B*2*n*n*128/1e9:.0f} GFLOP recomputed)")
     vv = torch.nn.functional.conv2d(fm, w_v).view(B, 128, n)
     ms = timeit(lambda: sb.gma.attn_matmul_v(attn.view(B, n, n), vv, residual=fm.view(B, 128, n), gamma=gam), n=10)
     report("gma attn @ v (tf32 tcgen05)", ms, B * (n * n * 4 + 3 * n * 128 * 4))

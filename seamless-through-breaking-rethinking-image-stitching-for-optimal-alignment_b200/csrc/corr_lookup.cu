@@ -203,6 +203,7 @@ corr_lookup_r4_kernel(const __grid_constant__ LookupMaps maps, const float* __re
                       const float* __restrict__ coords, float* __restrict__ out, int B, int HW1,
                       int H2, int W2, float coord_scale, int out_stride, int out_offset, int vec_out,
                       int sbq, unsigned int* dbg) {
+  asm volatile("griddepcontrol.launch_dependents;");   // the next kernel's CTAs may take freed SMs early (see the wait below)
   extern __shared__ __align__(128) unsigned char s_raw[];
   constexpr int kBufs = kFastDepth + 1;
   constexpr unsigned kFull = 0xffffffffu;
@@ -262,6 +263,11 @@ corr_lookup_r4_kernel(const __grid_constant__ LookupMaps maps, const float* __re
     return S;
   };
 
+  // Programmatic dependent launch (SB_TUNE_LOOKUP_PDL): everything above — barrier init, tensor-map
+  // prefetch, index setup — may run while the previous kernel on the stream drains; the first read of
+  // data a predecessor may have produced (coords; the volume through TMA later) waits here.  A no-op
+  // when the kernel is launched without the attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   FastSb cur = load_sb(0), nxt = load_sb(1);
   int t_cur = 0;                               // superblock of the group being sampled
   int f_t = 0, f_in = 0, f_buf = 0;            // front cursor: superblock, group in it, ring slot
@@ -524,10 +530,20 @@ extern "C" int sb_corr_lookup(const float* cost_maps, const float* coords, float
       if (sbq < D * kFastQ) sbq = 16;                                                                \
       const long long n_sb = (long long)B * ((hw1 + sbq - 1) / sbq);                                 \
       long long ctas = n_sb < (long long)kNumSMs * per_sm ? n_sb : (long long)kNumSMs * per_sm;      \
-      corr_lookup_r4_kernel<D><<<(int)ctas, kLookupWarps * 32, fast_smem_bytes(D), as_stream(stream)>>>( \
-          maps, cost_maps, coords, out, B, hw1, H2, W2, coord_scale, out_stride, out_offset, vec_out, \
-          sbq | (tune_get(SB_TUNE_LOOKUP_FETCH_ONLY, 0) ? 0x100 : 0) |                              \
-              ((tune_get(SB_TUNE_LOOKUP_L2_KEEP_EIGHTHS, 3) & 0xf) << 12), dbg_word);                                                                            \
+      const int sbq_arg = sbq | (tune_get(SB_TUNE_LOOKUP_FETCH_ONLY, 0) ? 0x100 : 0) |              \
+                          ((tune_get(SB_TUNE_LOOKUP_L2_KEEP_EIGHTHS, 3) & 0xf) << 12);              \
+      cudaLaunchConfig_t cfg = {};                                                                   \
+      cfg.gridDim = dim3((unsigned)ctas);                                                            \
+      cfg.blockDim = dim3(kLookupWarps * 32);                                                        \
+      cfg.dynamicSmemBytes = fast_smem_bytes(D);                                                     \
+      cfg.stream = as_stream(stream);                                                                \
+      cudaLaunchAttribute pdl_attr[1];                                                               \
+      pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                           \
+      pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;                                    \
+      cfg.attrs = pdl_attr;                                                                          \
+      cfg.numAttrs = tune_get(SB_TUNE_LOOKUP_PDL, 0) ? 1 : 0;                                        \
+      SB_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_r4_kernel<D>, maps, cost_maps, coords, out, B, hw1, H2, W2, \
+                                 coord_scale, out_stride, out_offset, vec_out, sbq_arg, dbg_word)); \
     } while (0)
     if (depth == 1) SB_LAUNCH_R4(1);
     else SB_LAUNCH_R4(2);

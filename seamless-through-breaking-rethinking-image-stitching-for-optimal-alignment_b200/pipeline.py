@@ -17,6 +17,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import collections
+
 import torch
 
 from . import corr as corr_mod
@@ -117,6 +119,7 @@ class HotPath:
         # the GPU co-schedules the two; inside a captured graph this is a fork/join of two branches.
         self.overlap = overlap
         self._side = None
+        self._inflight = collections.deque()              # "step done" events of eager steps (see step())
         # bench.py sets this to a list to get (start, stop) CUDA events around every launch of
         # the dominant kernel (the tcgen05 cost volume) on the launching stream
         self.gemm_events = None
@@ -208,22 +211,33 @@ class HotPath:
                     cost_pyramid_back=pyr_b)
 
     def step(self, pb: PairBatch):
+        cur = torch.cuda.current_stream()
+        eager = not torch.cuda.is_current_stream_capturing()
+        if eager and len(self._inflight) >= 2:
+            # At most two eager steps in flight: a host that runs further ahead of the GPU frees result
+            # blocks that crossed streams (record_stream below) long before they can be reused, and the
+            # caching allocator then falls back to cudaMalloc, which synchronises the device — measured
+            # 6.8 ms per step instead of 1.5 ms (tools/eager_alloc_dbg.py).  Not reached in a captured graph.
+            self._inflight.popleft().synchronize()
         if not self.overlap:
             out = self._cost_stage(pb)
             out.update(self._warp_stage(pb))
-            return out
-        cur = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = torch.cuda.Stream(pb.image1.device)
-        side = self._side
-        side.wait_stream(cur)                             # fork
-        with torch.cuda.stream(side):
-            wout = self._warp_stage(pb)
-        out = self._cost_stage(pb)
-        cur.wait_stream(side)                             # join
-        for v in wout.values():
-            v.record_stream(cur)                          # produced on `side`, consumed on `cur`
-        out.update(wout)
+        else:
+            if self._side is None:
+                self._side = torch.cuda.Stream(pb.image1.device)
+            side = self._side
+            side.wait_stream(cur)                             # fork
+            with torch.cuda.stream(side):
+                wout = self._warp_stage(pb)
+            out = self._cost_stage(pb)
+            cur.wait_stream(side)                             # join
+            for v in wout.values():
+                v.record_stream(cur)                          # produced on `side`, consumed on `cur`
+            out.update(wout)
+        if eager:
+            done = torch.cuda.Event()
+            done.record(cur)
+            self._inflight.append(done)
         return out
 
 

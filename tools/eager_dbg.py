@@ -24,3 +24,18 @@ for _ in range(20): C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_
 th = time.perf_counter() - t0
 torch.cuda.synchronize()
 print(f"corr_from_tokens host enqueue {th/20*1e3:.3f} ms/call")
+vol, lv = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_levels=3)
+maps = vol.view(16 * 4096, 1, 64, 64)
+torch.cuda.synchronize()
+for name, fn in (("encode_flow_token", lambda: sb.encode_flow_token(maps, pb.coords[0])),
+                 ("tokens_bf16", lambda: C.tokens_bf16(pb.fmap1)),
+                 ("warp", lambda: sb.warp(torch.cat([pb.image1, pb.image1], 1), pb.flow_ij)),
+                 ("empty 1GiB", lambda: torch.empty((16, 4096, 4096), device="cuda"))):
+    fn(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20): r = fn()
+    th = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    tt = time.perf_counter() - t0
+    print(f"{name}: host enqueue {th/20*1e6:.1f} us/call, with sync {tt/20*1e6:.1f} us/call")
+print(torch.cuda.memory_stats()["num_alloc_retries"], torch.cuda.memory_reserved() / 2**30)

@@ -21,6 +21,11 @@ fm = rnd(B, 128, 64, 64)
 w_qk, w_v, gam = rnd(256, 128, 1, 1) * 0.02, rnd(128, 128, 1, 1) * 0.09, torch.tensor([0.5], device="cuda")
 um = rnd(B, 576, 64, 64)
 cf1, cf2 = torch.relu(rnd(B, 1024, 32, 32)), torch.relu(rnd(B, 1024, 32, 32))
+ys13, xs13 = torch.meshgrid(torch.linspace(-1, 1, 13, device="cuda"), torch.linspace(-1, 1, 13, device="cuda"), indexing="ij")
+tps_src = torch.stack([xs13, ys13], -1).reshape(1, -1, 2).repeat(B, 1, 1)
+tps_tgt = tps_src + 0.02 * rnd(B, 169, 2)
+k_src = tps_src * 0.48 + 0.5
+k_w, k_a = 0.01 * rnd(B, 169, 2), torch.tensor([[0.01, -0.02], [1.0, 0.01], [-0.01, 1.0]], device="cuda").repeat(B, 1, 1)
 for rep in range(2):
     t1, t2 = C.tokens_bf16(f1), C.tokens_bf16(f2)
     vol, lv = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_levels=3)
@@ -36,5 +41,7 @@ for rep in range(2):
     del attn
     up = sb.decoder.upsample_flow(coords - sb.lookup.coords_grid(B, 64, 64, device="cuda"), um)
     cc = sb.udis2_homography.CCL(cf1, cf2)
+    tp = sb.torch_tps_transform.transformer(x6, tps_src, tps_tgt, (S, S))
+    tk = sb.kornia_tps.warp_image_tps(x6, k_src, k_w, k_a)
     torch.cuda.synchronize()
 print("ok")

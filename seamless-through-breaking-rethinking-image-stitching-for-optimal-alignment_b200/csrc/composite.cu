@@ -177,7 +177,7 @@ extern "C" int sb_composite_test_out(const float* homo1, const float* homo2, con
                                      int W, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  
+
   SB_REQUIRE(B >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_composite_test_out: bad size");
   const long long plane = (long long)H * W, total = plane * B;
   if (total == 0) return SB_OK;
@@ -195,7 +195,7 @@ extern "C" int sb_build_model(const float* warp1, const float* warp2, const floa
                               sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  
+
   SB_REQUIRE(B >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_build_model: bad size");
   const long long plane = (long long)H * W, total = plane * B * 3;
   if (total == 0) return SB_OK;
@@ -213,7 +213,7 @@ extern "C" int sb_tps_mix_blend(const float* final_warp, const float* tps_warp,
                                 sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  
+
   SB_REQUIRE(B >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_tps_mix_blend: bad size");
   const long long plane = (long long)H * W, total = plane * B;
   if (total == 0) return SB_OK;
@@ -229,7 +229,7 @@ extern "C" int sb_overlap_mask(const float* final_warp, float* overlap, int B, i
                                sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  
+
   SB_REQUIRE(B >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_overlap_mask: bad size");
   const long long plane = (long long)H * W, total = plane * B;
   if (total == 0) return SB_OK;

@@ -477,6 +477,43 @@ bilinear_sampler_kernel(const float* __restrict__ img, const float* __restrict__
   }
 }
 
+// Launch of the r = 4 kernel with D window groups in flight per warp: persistent grid sized for
+// `per_sm` resident CTAs per SM, superblock size by problem size, tuning knobs folded into `sbq`.
+template <int D>
+static int launch_r4(const LookupMaps& maps, const float* cost_maps, const float* coords, float* out, int B, int hw1,
+                     int H2, int W2, float coord_scale, int out_stride, int out_offset, int vec_out, int per_sm,
+                     long long nq, unsigned int* dbg_word, sb_stream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA(cudaFuncSetAttribute(corr_lookup_r4_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 fast_smem_bytes(D)));
+    attr_set = true;
+  }
+  if (per_sm <= 0) per_sm = (D == 1) ? 3 : 2;
+  const long long resident_warps = (long long)kNumSMs * per_sm * kLookupWarps;
+  int sbq = tune_get(SB_TUNE_LOOKUP_SUPERBLOCK, 0);
+  if (sbq != 8 && sbq != 16 && sbq != 32)
+    sbq = (nq >= resident_warps * 24) ? 32 : (nq >= resident_warps * 12 ? 16 : 8);
+  if (sbq < D * kFastQ) sbq = 16;
+  const long long n_sb = (long long)B * ((hw1 + sbq - 1) / sbq);
+  const long long ctas = n_sb < (long long)kNumSMs * per_sm ? n_sb : (long long)kNumSMs * per_sm;
+  const int sbq_arg = sbq | (tune_get(SB_TUNE_LOOKUP_FETCH_ONLY, 0) ? 0x100 : 0) |
+                      ((tune_get(SB_TUNE_LOOKUP_L2_KEEP_EIGHTHS, 3) & 0xf) << 12);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(kLookupWarps * 32);
+  cfg.dynamicSmemBytes = fast_smem_bytes(D);
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = pdl_attr;
+  cfg.numAttrs = tune_get(SB_TUNE_LOOKUP_PDL, 0) ? 1 : 0;
+  SB_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_r4_kernel<D>, maps, cost_maps, coords, out, B, hw1, H2, W2, coord_scale,
+                             out_stride, out_offset, vec_out, sbq_arg, dbg_word));
+  return SB_OK;
+}
+
 }  // namespace sb
 
 extern "C" int sb_corr_lookup(const float* cost_maps, const float* coords, float* out, int B,
@@ -484,7 +521,7 @@ extern "C" int sb_corr_lookup(const float* cost_maps, const float* coords, float
                               int out_stride, int out_offset, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  
+
   SB_REQUIRE(B >= 0 && H1 >= 0 && W1 >= 0 && H2 > 0 && W2 > 0, SB_EINVAL,
              "sb_corr_lookup: bad size");
   SB_REQUIRE(r >= 0 && r <= kMaxR, SB_EUNSUP, "sb_corr_lookup: r=%d outside [0,%d]", r, kMaxR);
@@ -514,40 +551,11 @@ extern "C" int sb_corr_lookup(const float* cost_maps, const float* coords, float
                                     CU_TENSOR_MAP_L2_PROMOTION_NONE, "cost_maps");
       if (rc != SB_OK) return rc;
     }
-#define SB_LAUNCH_R4(D)                                                                              \
-    do {                                                                                             \
-      static bool attr_set = false;                                                                  \
-      if (!attr_set) {                                                                               \
-        SB_CUDA(cudaFuncSetAttribute(corr_lookup_r4_kernel<D>,                                       \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, fast_smem_bytes(D))); \
-        attr_set = true;                                                                             \
-      }                                                                                              \
-      if (per_sm <= 0) per_sm = (D == 1) ? 3 : 2;                                                                   \
-      const long long resident_warps = (long long)kNumSMs * per_sm * kLookupWarps;                    \
-      int sbq = tune_get(SB_TUNE_LOOKUP_SUPERBLOCK, 0);                                              \
-      if (sbq != 8 && sbq != 16 && sbq != 32)                                                        \
-        sbq = (nq >= resident_warps * 24) ? 32 : (nq >= resident_warps * 12 ? 16 : 8);               \
-      if (sbq < D * kFastQ) sbq = 16;                                                                \
-      const long long n_sb = (long long)B * ((hw1 + sbq - 1) / sbq);                                 \
-      long long ctas = n_sb < (long long)kNumSMs * per_sm ? n_sb : (long long)kNumSMs * per_sm;      \
-      const int sbq_arg = sbq | (tune_get(SB_TUNE_LOOKUP_FETCH_ONLY, 0) ? 0x100 : 0) |              \
-                          ((tune_get(SB_TUNE_LOOKUP_L2_KEEP_EIGHTHS, 3) & 0xf) << 12);              \
-      cudaLaunchConfig_t cfg = {};                                                                   \
-      cfg.gridDim = dim3((unsigned)ctas);                                                            \
-      cfg.blockDim = dim3(kLookupWarps * 32);                                                        \
-      cfg.dynamicSmemBytes = fast_smem_bytes(D);                                                     \
-      cfg.stream = as_stream(stream);                                                                \
-      cudaLaunchAttribute pdl_attr[1];                                                               \
-      pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                           \
-      pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;                                    \
-      cfg.attrs = pdl_attr;                                                                          \
-      cfg.numAttrs = tune_get(SB_TUNE_LOOKUP_PDL, 0) ? 1 : 0;                                        \
-      SB_CUDA(cudaLaunchKernelEx(&cfg, corr_lookup_r4_kernel<D>, maps, cost_maps, coords, out, B, hw1, H2, W2, \
-                                 coord_scale, out_stride, out_offset, vec_out, sbq_arg, dbg_word)); \
-    } while (0)
-    if (depth == 1) SB_LAUNCH_R4(1);
-    else SB_LAUNCH_R4(2);
-#undef SB_LAUNCH_R4
+    const int rc4 = depth == 1 ? launch_r4<1>(maps, cost_maps, coords, out, B, hw1, H2, W2, coord_scale, out_stride,
+                                               out_offset, vec_out, per_sm, nq, dbg_word, stream)
+                               : launch_r4<2>(maps, cost_maps, coords, out, B, hw1, H2, W2, coord_scale, out_stride,
+                                               out_offset, vec_out, per_sm, nq, dbg_word, stream);
+    if (rc4 != SB_OK) return rc4;
     SB_LAUNCH_CHECK("corr_lookup_r4_kernel");
     return SB_OK;
   }
@@ -561,7 +569,7 @@ extern "C" int sb_bilinear_sampler(const float* img, const float* coords, float*
                                    int H, int W, int Ho, int Wo, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  
+
   SB_REQUIRE(N >= 0 && C >= 0 && H > 0 && W > 0 && Ho >= 0 && Wo >= 0, SB_EINVAL,
              "sb_bilinear_sampler: bad size");
   SB_REQUIRE((long long)H * W < (1ll << 31), SB_EUNSUP, "sb_bilinear_sampler: plane too large");

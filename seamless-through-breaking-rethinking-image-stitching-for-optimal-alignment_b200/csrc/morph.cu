@@ -163,7 +163,7 @@ extern "C" int sb_morph_open(const float* mask, float* out, int P, int H, int W,
                              int border_is_zero, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  
+
   SB_REQUIRE(P >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_morph_open: bad size");
   SB_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1), SB_EUNSUP,
              "sb_morph_open: kernel %dx%d must be odd", kh, kw);

@@ -76,7 +76,7 @@ extern "C" int sb_range_map(const float* flow, unsigned long long* accum, float*
                             int H, int W, int mode, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  
+
   SB_REQUIRE(B >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_range_map: bad size");
   SB_REQUIRE(mode >= 0 && mode <= 3, SB_EINVAL, "sb_range_map: mode %d", mode);
   SB_REQUIRE((long long)H * W < (1ll << 31), SB_EUNSUP, "sb_range_map: plane too large");

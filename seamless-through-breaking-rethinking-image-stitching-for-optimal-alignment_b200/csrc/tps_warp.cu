@@ -332,7 +332,7 @@ extern "C" int sb_tps_warp(const float* U, const float* T, const float* source, 
                            int W, int Hout, int Wout, int pn, sb_stream_t stream) {
   using namespace sb;
   SB_ENTER();
-  
+
   SB_REQUIRE(B >= 0 && C >= 0 && H > 0 && W > 0 && Hout >= 0 && Wout >= 0 && pn >= 0, SB_EINVAL,
              "sb_tps_warp: bad size");
   SB_REQUIRE(pn <= kTpsMaxPn, SB_EUNSUP, "sb_tps_warp: pn=%d > %d control points", pn, kTpsMaxPn);

@@ -1,4 +1,5 @@
-"""Launches each hot kernel twice at BASELINE config-2 size; run under ncu (-k regex ...)."""
+"""Launches each hot kernel twice at BASELINE config-2 size; run under ncu (-k regex ... --profile-from-start off):
+the first repetition is a warm-up outside the profiled range (cudaProfilerStart / Stop around the second)."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,6 +28,9 @@ tps_tgt = tps_src + 0.02 * rnd(B, 169, 2)
 k_src = tps_src * 0.48 + 0.5
 k_w, k_a = 0.01 * rnd(B, 169, 2), torch.tensor([[0.01, -0.02], [1.0, 0.01], [-0.01, 1.0]], device="cuda").repeat(B, 1, 1)
 for rep in range(2):
+    if rep == 1:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     t1, t2 = C.tokens_bf16(f1), C.tokens_bf16(f2)
     vol, lv = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_levels=3)
     vol0 = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64))
@@ -44,4 +48,5 @@ for rep in range(2):
     tp = sb.torch_tps_transform.transformer(x6, tps_src, tps_tgt, (S, S))
     tk = sb.kornia_tps.warp_image_tps(x6, k_src, k_w, k_a)
     torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok")

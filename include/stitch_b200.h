@@ -69,6 +69,7 @@ enum {
   SB_TUNE_CORR_STORE_POLICY = 7,   /* cost volume: L2 policy of the output stores: 1 evict_first (default), 2 evict_last, 3 none */
   SB_TUNE_TPS_LOG = 8,             /* TPS basis log(): 0 = lg2.approx * ln2 (default), 1 = libdevice logf */
   SB_TUNE_LOOKUP_PDL = 9,          /* r = 4 lookup launched with programmatic stream serialization (prologue overlaps the previous kernel's tail): 0 off, 1 on */
+  SB_TUNE_CORR_A_TMEM = 10,        /* cost volume: 1 = the A block is copied to tensor memory once per unit and the MMAs read it from there */
   SB_TUNE_COUNT = 16
 };
 int sb_tune(int key, int value);

@@ -150,7 +150,11 @@ __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, 2 ulp; -inf -> 
 //       are merged through shared memory;
 //   2 = normalise: the contraction is recomputed and every value leaves as
 //       tf32(exp(x - max) / sum) through the usual staged TMA stores.
-template <int POOL, bool BF16OUT = false, bool TWO_CTA = false, int SMX = 0>
+// ATMEM (POOL 0 / 1, one CTA per tile, no SMX): the unit's A block (128 queries x C channels) is copied from
+// shared memory into tensor memory ONCE per unit (tcgen05.cp, 8 columns per K = 16 step, columns 384..511;
+// three accumulator buffers instead of four) and every MMA reads A from there: the shared-memory pipe, the
+// busiest unit of this kernel (ncu: 75-78 %), loses 48 of its ~320 KB per tile.
+template <int POOL, bool BF16OUT = false, bool TWO_CTA = false, int SMX = 0, bool ATMEM = false>
 __global__ void __launch_bounds__(SMX == 1 ? 384 : 256, 1)
 corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_l1,
@@ -181,6 +185,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const long long unit0 = TWO_CTA ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
   const long long unit_step = TWO_CTA ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
   constexpr int kBRows = TWO_CTA ? BN / 2 : BN;                   // B rows this CTA loads per tile
+  constexpr int kNAcc = ATMEM ? 3 : kAccBufs;                     // accumulator buffers in use
+  static_assert(!ATMEM || (POOL != 2 && !TWO_CTA && SMX == 0), "ATMEM: one CTA per tile, POOL 0 / 1 only");
   constexpr int kBPanelBytes = kBRows * 128;
 
   if (warp == 0 && lane == 0) {
@@ -265,6 +271,17 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int t1 = min(t0 + p.tpu, p.NT);
         ptx::mbar_wait(bar_a_full, a_par, 3, p.dbg);
         a_par ^= 1;
+        const uint32_t a_tmem = tmem_base + 3 * BN;      // ATMEM: columns 384..511
+        if (ATMEM) {
+          ptx::tc_fence_after_sync();
+          for (int kp = 0; kp < p.KP; ++kp) {
+            const uint64_t adesc = ptx::umma_desc_k_sw128(sA + kp * kPanelBytes);
+#pragma unroll
+            for (int k = 0; k < BKP / 16; ++k)
+              ptx::tmem_cp_128x256b(a_tmem + (uint32_t)(kp * (BKP / 16) + k) * 8u, adesc + 2 * k);
+          }
+          ptx::umma_commit(bar_a_empty);                 // the A block in shared memory is free once the copies retire
+        }
         for (int t = t0; t < t1; ++t) {
           ptx::mbar_wait(bar_t_empty + 8 * acc, acc_par ^ 1, 4, p.dbg);
           ptx::mbar_wait(bar_b_full + 8 * stage, b_par, 5, p.dbg);
@@ -278,6 +295,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int k = 0; k < BKP / 16; ++k) {
               // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
               if (TWO_CTA) ptx::umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc2, (kp | k) != 0);
+              else if (ATMEM) ptx::umma_f16_ts(d_tmem, a_tmem + (uint32_t)(kp * (BKP / 16) + k) * 8u, bdesc + 2 * k, kIdesc, (kp | k) != 0);
               else ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kp | k) != 0);
             }
           }
@@ -289,10 +307,10 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             ptx::umma_commit(bar_t_full + 8 * acc);      // accumulator ready for the epilogue
           }
           if (++stage == kStages) { stage = 0; b_par ^= 1; }
-          if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
+          if (++acc == kNAcc) { acc = 0; acc_par ^= 1; }
         }
         if (TWO_CTA) ptx::umma_commit_2cta(bar_a_empty, 3);
-        else ptx::umma_commit(bar_a_empty);             // A reusable once the unit's MMAs retire
+        else if (!ATMEM) ptx::umma_commit(bar_a_empty);  // A reusable once the unit's MMAs retire
       }
     }
     __syncwarp();
@@ -590,7 +608,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (TWO_CTA) ptx::mbar_arrive_cluster(ptx::mapa_shared(bar_t_empty + 8 * acc, 0));   // the leader's barrier
           else ptx::mbar_arrive(bar_t_empty + 8 * acc);
         }
-        if (++acc == kAccBufs) { acc = 0; acc_par ^= 1; }
+        if (++acc == kNAcc) { acc = 0; acc_par ^= 1; }
 
         if (POOL == 1) {
           if (p.lvl1) {
@@ -895,6 +913,7 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     p.store_policy = ((tp & 3) == 3 ? 0 : (tp & 3)) | (tp & 4);
   }
 
+  const bool a_tmem = tune_get(SB_TUNE_CORR_A_TMEM, 0) == 1 && !two_cta && !bf16_out && !smx_stats && pool_mode != 2;
   const int grid = (int)((p.n_units < kNumSMs) ? p.n_units : kNumSMs);
   static bool attr_set = false;
   if (!attr_set) {
@@ -905,6 +924,8 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, false, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<1, false, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     attr_set = true;
@@ -938,8 +959,12 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     corr_umma_kernel<0, true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
   else if (pool_mode == 2)
     corr_umma_kernel<2><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
+  else if (fused_pool && a_tmem)
+    corr_umma_kernel<1, false, false, 0, true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
   else if (fused_pool)
     corr_umma_kernel<1><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
+  else if (a_tmem)
+    corr_umma_kernel<0, false, false, 0, true><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
   else
     corr_umma_kernel<0><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
   SB_LAUNCH_CHECK("corr_umma_kernel");

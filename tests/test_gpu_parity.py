@@ -93,6 +93,30 @@ def test_corr_cta_pair_mode_is_bit_identical(sb):
         lib.sb_tune(6, 0)
 
 
+def test_corr_a_operand_from_tensor_memory_is_bit_identical(sb):
+    """A block copied to TMEM once per unit (tcgen05.cp) and read by the TS form of tcgen05.mma (opt-in
+    through sb_tune): same bits as the shared-memory-operand kernel; ragged shapes, C = 96 (padded K) and 256."""
+    lib = sb._lib.load()
+    gen = torch.Generator().manual_seed(15)
+    try:
+        for b, c, hw, lv in ((1, 256, (9, 20), 0), (2, 256, (64, 64), 3), (1, 96, (24, 40), 0), (3, 128, (20, 32), 0)):
+            f1 = torch.randn(b, c, *hw, generator=gen)
+            f2 = torch.randn(b, c, *hw, generator=gen)
+            t1, t2 = sb.corr.tokens_bf16(cu(f1)), sb.corr.tokens_bf16(cu(f2))
+            res = []
+            for mode in (0, 1):
+                lib.sb_tune(10, mode)
+                res.append(sb.corr.corr_from_tokens(t1, t2, c, hw, hw, pyramid_levels=lv))
+            if lv:
+                assert torch.equal(res[0][0], res[1][0])
+                for x, y in zip(res[0][1], res[1][1]):
+                    assert torch.equal(x, y)
+            else:
+                assert torch.equal(res[0], res[1])
+    finally:
+        lib.sb_tune(10, 0)
+
+
 def test_corr_odd_token_count(sb):
     """13 x 15 = 195 target tokens (not a multiple of 4): pitched volume, strided view of the reference's shape."""
     gen = torch.Generator().manual_seed(9)

@@ -51,6 +51,9 @@ int sb_device_check(void);
  * (bench.py's "gpu_launches"). */
 long long sb_launch_count(void);
 void sb_reset_launch_count(void);
+/* Frees the library's own state (a 64-byte mapped debug word), resets sb_tune knobs and the launch counter.
+ * Everything else (outputs, workspaces, sb_host_alloc blocks) is caller-owned.  The library stays usable. */
+int sb_shutdown(void);
 /* Pinned (page-locked, portable) host buffers for the host-resident data path; write_combined != 0
  * adds cudaHostAllocWriteCombined (CPU fills sequentially, device reads). NULL on failure. */
 void* sb_host_alloc(size_t bytes, int write_combined);

@@ -28,6 +28,7 @@ SIGNATURES = {
     "sb_device_check": (c_int, []),
     "sb_launch_count": (c_longlong, []),
     "sb_reset_launch_count": (None, []),
+    "sb_shutdown": (c_int, []),
     "sb_debug_word": (c_uint, []),
     "sb_tune": (c_int, [c_int, c_int]),
     "sb_host_alloc": (c_void_p, [c_size_t, c_int]),

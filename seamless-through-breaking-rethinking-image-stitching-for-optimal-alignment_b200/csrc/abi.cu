@@ -113,5 +113,22 @@ int sb_host_free(void* p) {
   return SB_OK;
 }
 void sb_reset_launch_count(void) { sb::g_launches.store(0, std::memory_order_relaxed); }
+// Releases what the library itself holds (the 64-byte mapped debug word) and resets the tuning knobs and
+// the launch counter.  Outputs, workspaces and sb_host_alloc blocks belong to the caller.  The library can be
+// used again afterwards (state is re-created on demand).
+int sb_shutdown(void) {
+  for (int k = 0; k < SB_TUNE_COUNT; ++k) sb::g_tune[k].store(0, std::memory_order_relaxed);
+  sb::g_launches.store(0, std::memory_order_relaxed);
+  if (sb::g_dbg_host) {
+    cudaError_t e = cudaFreeHost(sb::g_dbg_host);
+    sb::g_dbg_host = nullptr;
+    sb::g_dbg = nullptr;
+    if (e != cudaSuccess) {
+      sb::set_error("sb_shutdown: cudaFreeHost failed: %s", cudaGetErrorString(e));
+      return SB_ECUDA;
+    }
+  }
+  return SB_OK;
+}
 
 }  // extern "C"

@@ -607,6 +607,20 @@ def test_ccl_shapes(sb, h, w):
     assert max_abs(got, ref) <= 1e-2 * max(1.0, max(h, w) / 12.0), max_abs(got, ref)
 
 
+def test_shutdown_releases_library_state_and_library_stays_usable(sb):
+    lib = sb._lib.load()
+    x = torch.rand(1, 3, 16, 16, device="cuda")
+    flo = torch.zeros(1, 2, 16, 16, device="cuda")
+    a = sb.warp(x, flo)
+    lib.sb_tune(0, 1)
+    assert lib.sb_shutdown() == 0 and lib.sb_shutdown() == 0        # idempotent
+    assert lib.sb_launch_count() == 0
+    cm = torch.rand(64, 1, 8, 8, device="cuda")
+    tok = sb.encode_flow_token(cm, sb.lookup.coords_grid(1, 8, 8, device="cuda"))   # needs the debug word again
+    assert tuple(tok.shape) == (1, 81, 8, 8)
+    assert torch.equal(sb.warp(x, flo), a)
+
+
 def test_next_rows_empty_and_bad_inputs(sb):
     """Empty batches return empty results of the reference's shape; wrong devices / shapes raise."""
     z = lambda *sh: torch.zeros(*sh, device="cuda")

@@ -10,6 +10,8 @@ parity contract: 1e-2 relative to the volume's scale).
 """
 from __future__ import annotations
 
+import sys
+
 import torch
 
 from . import _lib
@@ -139,3 +141,14 @@ def corr_from_tokens(tok1: torch.Tensor, tok2: torch.Tensor, c: int, hw1, hw2, p
     _lib.check(rc, "sb_corr_tokens")
     out = vol.view(b, 1, h1, w1, h2, w2)
     return (out, lv[:pyramid_levels]) if pyramid_levels else out
+
+
+class _CallableModule(type(sys)):
+    """``stitch_b200.corr(fmap1, fmap2, heads=1)`` — the package-level name SURVEY §8(b) asks for — and the
+    module ``stitch_b200.corr`` (``corr.corr``, ``corr.tokens_bf16`` ...) are the same object."""
+
+    def __call__(self, *args, **kwargs):
+        return corr(*args, **kwargs)
+
+
+sys.modules[__name__].__class__ = _CallableModule

@@ -121,3 +121,14 @@ def test_header_is_plain_c():
         inc = os.path.join(ROOT, "include")
         subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, path], check=True)
         subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", inc, path], check=True)
+
+
+def test_package_level_corr_is_callable_and_a_module():
+    """`corr(fmap1, fmap2, heads=1)` at package level; `stitch_b200.corr` is also the module."""
+    import inspect
+    import torch
+    import stitch_b200 as sb
+    assert callable(sb.corr) and inspect.ismodule(sb.corr)
+    assert list(inspect.signature(sb.corr.corr).parameters)[:3] == ["fmap1", "fmap2", "heads"]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sb.corr(torch.zeros(1, 8, 4, 4), torch.zeros(1, 8, 4, 4))

@@ -126,6 +126,17 @@ def cpu_pairs_per_s(n_pairs, min_seconds, max_seconds=60.0):
     return done / el, done
 
 
+def cpu_model() -> str:
+    """CPU model string of the host the CPU legs ran on (reported with the numbers)."""
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.lower().startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path. The reference is
     pure Python and cannot travel to the GPU box (no /root/reference there), so the timed code is
@@ -147,7 +158,7 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.gpus), "note": "CPU arm: each step is a bounded sample of "
                    f"{sample_pairs} pairs of the same workload on the host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(),
                          "sample": f"{sample_pairs} pairs per step x {args.steps} steps, all host threads (OpenMP + BLAS)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -330,7 +341,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, done = cpu_pairs_per_s(2, 12.0)
-            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "cpu_model": cpu_model(),
                    "sample": f"{done} pairs of the same op list (oracle port: numpy BLAS + OpenMP C), all host threads"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -132,3 +132,17 @@ def test_package_level_corr_is_callable_and_a_module():
     assert list(inspect.signature(sb.corr.corr).parameters)[:3] == ["fmap1", "fmap2", "heads"]
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         sb.corr(torch.zeros(1, 8, 4, 4), torch.zeros(1, 8, 4, 4))
+
+
+def test_tune_knob_enum_is_consistent():
+    """SB_TUNE_* keys are unique, below SB_TUNE_COUNT, and sb_tune rejects anything else."""
+    hdr = open(os.path.join(ROOT, "include", "stitch_b200.h")).read()
+    keys = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"\b(SB_TUNE_[A-Z0-9_]+)\s*=\s*(\d+)", hdr))
+    count = keys.pop("SB_TUNE_COUNT")
+    assert len(keys) >= 10 and len(set(keys.values())) == len(keys) and max(keys.values()) < count
+    import stitch_b200 as sb
+    lib = sb._lib.load()
+    for v in keys.values():
+        assert lib.sb_tune(v, 0) == 0
+    assert lib.sb_tune(count, 1) != 0 and lib.sb_tune(-1, 1) != 0
+    assert b"unknown key" in lib.sb_last_error()

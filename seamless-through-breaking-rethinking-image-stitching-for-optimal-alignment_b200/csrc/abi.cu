@@ -1,6 +1,7 @@
 // abi.cu — library-wide state of libstitchb200: error string, device check,
 // launch counter.  No kernels here.
 #include <atomic>
+#include <mutex>
 #include <string.h>
 
 #include "common.cuh"
@@ -26,21 +27,31 @@ int tune_get(int key, int dflt) {
 
 // Word written (system scope) just before a protocol-timeout trap. It lives in
 // mapped pinned host memory so the host can still read it after the context died.
+// Portable: every device of the process (one host thread per GPU under nn.DataParallel) sees the
+// same mapped word; under unified addressing its device pointer is the same on all of them.
 static unsigned int* g_dbg_host = nullptr;
-static unsigned int* g_dbg = nullptr;
+static std::atomic<unsigned int*> g_dbg{nullptr};
+static std::mutex g_dbg_mutex;
 unsigned int* debug_word_device() {
-  if (!g_dbg) {
-    cudaError_t e = cudaHostAlloc(&g_dbg_host, 64, cudaHostAllocMapped);
-    if (e == cudaSuccess) {
-      *g_dbg_host = 0;
-      e = cudaHostGetDevicePointer(&g_dbg, g_dbg_host, 0);
-    }
-    if (e != cudaSuccess) {
-      set_error("debug word allocation failed: %s", cudaGetErrorString(e));
-      g_dbg = nullptr;
-    }
+  unsigned int* d = g_dbg.load(std::memory_order_acquire);
+  if (d) return d;
+  std::lock_guard<std::mutex> lock(g_dbg_mutex);
+  d = g_dbg.load(std::memory_order_relaxed);
+  if (d) return d;
+  unsigned int* h = nullptr;
+  cudaError_t e = cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e == cudaSuccess) {
+    *h = 0;
+    e = cudaHostGetDevicePointer(&d, h, 0);
+    if (e != cudaSuccess) cudaFreeHost(h);
   }
-  return g_dbg;
+  if (e != cudaSuccess) {
+    set_error("debug word allocation failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  g_dbg_host = h;
+  g_dbg.store(d, std::memory_order_release);
+  return d;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -119,10 +130,11 @@ void sb_reset_launch_count(void) { sb::g_launches.store(0, std::memory_order_rel
 int sb_shutdown(void) {
   for (int k = 0; k < SB_TUNE_COUNT; ++k) sb::g_tune[k].store(0, std::memory_order_relaxed);
   sb::g_launches.store(0, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lock(sb::g_dbg_mutex);
   if (sb::g_dbg_host) {
     cudaError_t e = cudaFreeHost(sb::g_dbg_host);
     sb::g_dbg_host = nullptr;
-    sb::g_dbg = nullptr;
+    sb::g_dbg.store(nullptr, std::memory_order_release);
     if (e != cudaSuccess) {
       sb::set_error("sb_shutdown: cudaFreeHost failed: %s", cudaGetErrorString(e));
       return SB_ECUDA;

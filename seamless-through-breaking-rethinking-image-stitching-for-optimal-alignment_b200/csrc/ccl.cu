@@ -400,10 +400,11 @@ extern "C" int sb_ccl(const float* feature_1, const float* feature_2, float* flo
   if (!dbg_word) return SB_ECUDA;
   if (C <= kTokMaxC && (N & 3) == 0 && aligned16(feature_1) && aligned16(feature_2)) {
     const size_t smem = CclTokSmem::bytes(C);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    static SmemOptIn tok_opt_in;
+    int opt_dev;
+    if (tok_opt_in.need(smem, &opt_dev)) {
       SB_CUDA(cudaFuncSetAttribute(ccl_norm_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
+      tok_opt_in.done(smem, opt_dev);
     }
     const float* feats[2] = {feature_1, feature_2};
     float* toks[2] = {tok1, tok2};
@@ -431,10 +432,11 @@ extern "C" int sb_ccl(const float* feature_1, const float* feature_2, float* flo
   if (rc) return rc;
   if ((N & 3) == 0 && W <= 256) {
     const size_t smem = ((size_t)3 * kFlowBandRows * ccl_stage_cols((int)N, W) + (size_t)kFlowG * kFlowQC + 3 * kFlowQC + kFlowG * kFlowWarpsPerP * 4) * sizeof(float) + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static SmemOptIn staged_opt_in;
+    int opt_dev;
+    if (staged_opt_in.need(200 * 1024, &opt_dev)) {
       SB_CUDA(cudaFuncSetAttribute(ccl_flow_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
+      staged_opt_in.done(200 * 1024, opt_dev);
     }
     ccl_flow_staged_kernel<<<dim3((unsigned)((N + kFlowG - 1) / kFlowG), B), kFlowG * kFlowWarpsPerP * 32, smem, s>>>(c0, flow, H, W, softmax_scale, dbg_word);
     SB_LAUNCH_CHECK("ccl_flow_staged_kernel");
@@ -442,10 +444,11 @@ extern "C" int sb_ccl(const float* feature_1, const float* feature_2, float* flo
   }
   SB_REQUIRE(N <= 4096, SB_EUNSUP, "sb_ccl: more than 4096 positions with H*W %% 4 != 0 or W > 256 (8 rows of N floats must fit shared memory)");
   const size_t flow_smem = (size_t)8 * N * sizeof(float);
-  static size_t flow_smem_set = 0;
-  if (flow_smem > 48 * 1024 && flow_smem > flow_smem_set) {
+  static SmemOptIn flow_opt_in;
+  int flow_dev;
+  if (flow_smem > 48 * 1024 && flow_opt_in.need(flow_smem, &flow_dev)) {
     SB_CUDA(cudaFuncSetAttribute(ccl_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flow_smem));
-    flow_smem_set = flow_smem;
+    flow_opt_in.done(flow_smem, flow_dev);
   }
   ccl_flow_kernel<<<dim3((unsigned)((N + 7) / 8), B), 256, flow_smem, s>>>(c0, flow, H, W, softmax_scale);
   SB_LAUNCH_CHECK("ccl_flow_kernel");

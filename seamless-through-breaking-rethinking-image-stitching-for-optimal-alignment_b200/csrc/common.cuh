@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -55,6 +56,30 @@ int tune_get(int key, int dflt);   // sb_tune() override, else dflt
     int _rc = sb::check_device();          \
     if (_rc != SB_OK) return _rc;          \
   } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, and the library can be
+// driven by several host threads of one process, one per GPU (the reference's nn.DataParallel,
+// out.py:80 / evaluate.py:119).  One SmemOptIn per kernel family remembers, per device ordinal, the largest
+// opt-in made so far; two threads racing on the same device both make the (idempotent) call.
+class SmemOptIn {
+ public:
+  static constexpr int kMaxDevices = 64;
+  // true when `bytes` exceeds what has been configured on the calling thread's current device
+  bool need(size_t bytes, int* dev) {
+    *dev = -1;
+    if (cudaGetDevice(dev) != cudaSuccess || *dev < 0 || *dev >= kMaxDevices) return true;
+    return set_[*dev].load(std::memory_order_acquire) < bytes;
+  }
+  void done(size_t bytes, int dev) {
+    if (dev < 0 || dev >= kMaxDevices) return;
+    size_t cur = set_[dev].load(std::memory_order_relaxed);
+    while (cur < bytes && !set_[dev].compare_exchange_weak(cur, bytes, std::memory_order_release)) {
+    }
+  }
+
+ private:
+  std::atomic<size_t> set_[kMaxDevices] = {};
+};
 
 inline cudaStream_t as_stream(sb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

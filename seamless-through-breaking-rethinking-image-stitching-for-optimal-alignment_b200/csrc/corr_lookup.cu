@@ -483,11 +483,12 @@ template <int D>
 static int launch_r4(const LookupMaps& maps, const float* cost_maps, const float* coords, float* out, int B, int hw1,
                      int H2, int W2, float coord_scale, int out_stride, int out_offset, int vec_out, int per_sm,
                      long long nq, unsigned int* dbg_word, sb_stream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SmemOptIn opt_in;   // one per instantiation D
+  int opt_dev;
+  if (opt_in.need(fast_smem_bytes(D), &opt_dev)) {
     SB_CUDA(cudaFuncSetAttribute(corr_lookup_r4_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  fast_smem_bytes(D)));
-    attr_set = true;
+    opt_in.done(fast_smem_bytes(D), opt_dev);
   }
   if (per_sm <= 0) per_sm = (D == 1) ? 3 : 2;
   const long long resident_warps = (long long)kNumSMs * per_sm * kLookupWarps;

@@ -915,8 +915,9 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
 
   const bool a_tmem = tune_get(SB_TUNE_CORR_A_TMEM, 0) == 1 && !two_cta && !bf16_out && !smx_stats && pool_mode != 2;
   const int grid = (int)((p.n_units < kNumSMs) ? p.n_units : kNumSMs);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SmemOptIn opt_in;
+  int opt_dev;
+  if (opt_in.need(kSmemTotal, &opt_dev)) {
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
@@ -928,7 +929,7 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<1, false, false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(corr_umma_kernel<0, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    attr_set = true;
+    opt_in.done(kSmemTotal, opt_dev);
   }
   if (smx_stats) {
     // pass 1: one unit per row block, all NT tiles; pass 2: the usual units

@@ -342,14 +342,15 @@ static int launch_attn_v(const CUtensorMap& map_a, const CUtensorMap& map_b, Att
                          cudaStream_t stream) {
   p.dbg = debug_word_device();
   if (!p.dbg) return SB_ECUDA;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SmemOptIn opt_in;
+  int opt_dev;
+  if (opt_in.need(kGSmemTotal, &opt_dev)) {
     SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
     SB_CUDA(cudaFuncSetAttribute(attn_v_umma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmemTotal));
-    attr_set = true;
+    opt_in.done(kGSmemTotal, opt_dev);
   }
   const int grid = (int)(p.n_units < kNumSMs ? p.n_units : kNumSMs);
   if (bf16) {

@@ -322,6 +322,8 @@ def adapter_test_out():
 
 
 ADAPTER_SAMPLE = (slice(None, None, 3), slice(None, None, 3))
+# pixels of the test_out canvas whose compositing inputs AND outputs are stored (tests/golden/composite_w6.npz)
+W6_SAMPLE = (slice(1, None, 4), slice(2, None, 4))
 
 
 def to_numpy(d):

@@ -248,25 +248,46 @@ def main():
     arrays["grid"] = _k_warp_points_tps(coords, c["points_src"], kwt, awt).view(-1, c["image"].shape[2], c["image"].shape[3], 2).numpy()
     save("tps_kornia", cases.checksum(*c.values()), **arrays)
 
-    # ---------------------------------------------------------------- W8 (restated: tps_pipline.py needs matplotlib
-    # + cv2-contrib at import/run time; lines :139-170 are restated here with the same torch / cv2 calls)
-    import cv2
+    # ---------------------------------------------------------------- W8: the reference's own
+    # core/inference/tps_pipline.py:tps_H_warp, lines :138-170 executed as written.  matplotlib is absent
+    # (import-time stub; nothing of it runs with is_plot=False); the three stages UPSTREAM of :138
+    # (preprocess / sample_init_points / warp_by_tps: point sampling + the third-party OpenCV TPS, out of
+    # scope) are replaced by stubs that hand the case's seeded tensors to the real mix / open / blend code.
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    import core.inference.tps_pipline as ref_tp
     c = cases.tps_mix_small()
-    tm = c["tps_mask3"].mean(dim=1, keepdim=True)
-    tm = (tm >= 0.5).float()
-    inv = (1.0 - tm)[0, 0].numpy()
-    kernel = cv2.getStructuringElement(cv2.MORPH_RECT, (11, 11))
-    inv = cv2.dilate(cv2.erode(inv, kernel), kernel)
-    tm = 1.0 - torch.tensor(inv)[None, None]
-    tps_warp = c["tps_warp_raw"] * tm
-    fm = (c["final_warp"] >= 3).float().mean(dim=1, keepdim=True)
-    fm = (fm >= 0.5).float()
-    inv1 = ((1 - c["mask1"]).float().mean(dim=1, keepdim=True) >= 0.5).float()
-    tfw = c["final_warp"] * fm + tps_warp * (1 - fm) * inv1
-    tfm = fm + (1 - fm) * tm * inv1
-    out2 = tfw * tfm
-    blend = ((c["output1"] * c["mask1"] + out2 * tfm) / (c["mask1"] + tfm)).clip(0, 255).to(torch.uint8)
-    save("tps_mix", cases.checksum(*c.values()), tps_mask=tm.numpy(), output2=out2.numpy(), mask2=tfm.numpy(), blend=blend.numpy())
+    h, w = c["final_warp"].shape[-2:]
+    saved = (ref_tp.preprocess, ref_tp.sample_init_points, ref_tp.warp_by_tps, ref_tp.cv2)
+    opened = []                                  # result of the cv2.dilate at :146 (the opened inverse mask)
+
+    def _dilate(*a, **k):
+        opened.append(saved[3].dilate(*a, **k))
+        return opened[-1]
+    ref_tp.cv2 = SimpleNamespace(getStructuringElement=saved[3].getStructuringElement, MORPH_RECT=saved[3].MORPH_RECT,
+                                 erode=saved[3].erode, dilate=_dilate)
+    ref_tp.preprocess = lambda residual_flow, valid, **k: residual_flow
+    ref_tp.sample_init_points = lambda residual_flow, **k: (None, None, torch.zeros(1, 4, 2), torch.zeros(1, 4, 2))
+    ref_tp.warp_by_tps = lambda H_warp, H_warp_mask, ps, pd, **k: torch.cat((c["tps_warp_raw"].clone(), c["tps_mask3"].clone()), 1)
+    try:
+        od = ref_tp.tps_H_warp(
+            SimpleNamespace(output1=c["output1"].clone(), mask1=c["mask1"].clone(), H_warp=None, H_warp_mask=None,
+                            final_warp=c["final_warp"].clone(), mask2=None, residual_flow=torch.zeros(1, 2, h, w),
+                            valid=None, occlusion_mask=None, border_points_mask=None),
+            SimpleNamespace(width_min=0, height_min=0, out_height=h, out_width=w),
+            SimpleNamespace(grid_h=12, grid_w=12, pad_num=0, residual_flow_use_forward=False, flow_limit=None,
+                            add_corner=False, get_pt_methods=None, add_meshgrid=False, affine_scale=1.0,
+                            kernel_scale=1.0, use_boundary_limit=False, tps_method="opencv",
+                            output2_is_only_tps=False, do_avg_pooling=False),
+            inpaint_fn=None, is_plot=False)
+    finally:
+        ref_tp.preprocess, ref_tp.sample_init_points, ref_tp.warp_by_tps, ref_tp.cv2 = saved
+    assert len(opened) == 1
+    tm = 1.0 - torch.tensor(opened[0])[None, None]                               # :147-148
+    assert torch.equal(od["tps_output"], c["tps_warp_raw"] * tm)
+    save("tps_mix", cases.checksum(*c.values()), tps_mask=tm.numpy(), tps_output=od["tps_output"].numpy(),
+         output2=od["output2"].numpy(), mask2=od["mask2"].numpy(), blend=od["new_blend_image"].numpy())
 
     # ---------------------------------------------------------------- G1
     g = torch.Generator().manual_seed(77)
@@ -291,7 +312,38 @@ def main():
     c = cases.adapter_test_out()
     ad = ref_ad.FlowHomoAdpater(cases.StubHomo(c["offsets"]), cases.StubFlow(c["flows"]), cases.adapter_cfg())
     ad.eval()
-    od = ad.test_out_forward(c["image1"], c["image2"])
+    # W6: record what the reference's own compositing block (flowHomoAdpater.py:317,339-360) consumes, by
+    # spying on the three functions whose results feed it — transformer calls #2..#5 of test_out_forward are
+    # homo_output (:292), homo_output2 (:310), residual_flow_output (:314) and occlusion_mask (:335); warp is
+    # called once (:316); preprocess_occlusion_mask's second call (:336) yields the mask that multiplies (:339)
+    spy = dict(transformer=[], warp=[], morph=[])
+    orig = (ref_ad.torch_homo_transform.transformer, ref_ad.warp, ref_ad.preprocess_occlusion_mask)
+
+    def _spy(key, fn):
+        def wrapped(*a, **k):
+            r = fn(*a, **k)
+            spy[key].append(r.clone())
+            return r
+        return wrapped
+
+    ref_ad.torch_homo_transform.transformer = _spy("transformer", orig[0])
+    ref_ad.warp = _spy("warp", orig[1])
+    ref_ad.preprocess_occlusion_mask = _spy("morph", orig[2])
+    try:
+        od = ad.test_out_forward(c["image1"], c["image2"])
+    finally:
+        ref_ad.torch_homo_transform.transformer, ref_ad.warp, ref_ad.preprocess_occlusion_mask = orig
+    assert len(spy["transformer"]) == 5 and len(spy["warp"]) == 1 and len(spy["morph"]) == 2
+    w6 = dict(homo_output=spy["transformer"][1], homo_output2=spy["transformer"][2],
+              flow_mask=spy["transformer"][3][:, 2:3], warp_out=spy["warp"][0], occlusion_mask=spy["morph"][1])
+    w6["final_warp_in"] = w6["warp_out"] * w6["flow_mask"]                       # :317, the reference's own op
+    assert torch.equal(w6["occlusion_mask"], od["occlusion_mask"])
+    assert torch.equal((w6["final_warp_in"] * w6["occlusion_mask"])[:, 0:3], od["final_warp"])   # :339
+    wy, wx = cases.W6_SAMPLE                 # compositing is per pixel: a pixel subset is a complete test vector
+    w6_arrays = {k: v[..., wy, wx].contiguous().numpy() for k, v in w6.items()}
+    for k in ("final_warp", "output1", "output2", "mask1", "mask2", "blend_image"):
+        w6_arrays["out_" + k] = od[k][..., wy, wx].contiguous().numpy()
+    save("composite_w6", cases.checksum(c["image1"], c["image2"], c["offsets"], *c["flows"]), **w6_arrays)
     sy, sx = cases.ADAPTER_SAMPLE
     arrays = {}
     for k in ("H_warp", "final_warp", "output1", "output2", "mask1", "mask2", "H_warp_mask"):

@@ -16,10 +16,16 @@ def max_abs(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, (a.shape, b.shape)
-    both_nan = np.isnan(a) & np.isnan(b)
-    d = np.abs(a - b)
-    d[both_nan] = 0.0
-    return float(np.nanmax(d)) if d.size else 0.0
+    na, nb = np.isnan(a), np.isnan(b)
+    one_sided = int((na != nb).sum())
+    # a NaN on one side only is a mismatch, never something to skip over
+    assert one_sided == 0, f"{one_sided} of {a.size} elements are NaN on one side only"
+    # infinities must agree exactly (inf - inf would be NaN and hide a sign error)
+    ia, ib = np.isinf(a), np.isinf(b)
+    bad_inf = int(((ia | ib) & ~na & (a != b)).sum())
+    assert bad_inf == 0, f"{bad_inf} of {a.size} elements are infinite on one side only (or differ in sign)"
+    fin = ~(na | ia)
+    return float(np.abs(a[fin] - b[fin]).max()) if fin.any() else 0.0
 
 
 def assert_bits_equal(a, b, what=""):

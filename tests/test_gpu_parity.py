@@ -187,7 +187,9 @@ def test_corr_512_golden_and_pyramid(sb):
     # public pyramid API
     pyr = sb.corr_pyramid(cu(c["fmap1"]), cu(c["fmap2"]), 4)
     assert [tuple(p.shape) for p in pyr] == [(4096, 1, 64, 64), (4096, 1, 32, 32), (4096, 1, 16, 16), (4096, 1, 8, 8)]
-    assert pyr[0].data_ptr() != 0 and torch.equal(pyr[0].view(-1), vol.view(-1)) is not None
+    assert torch.equal(pyr[0].view(-1), vol.view(-1))      # level 0 of the public pyramid IS the volume
+    for p_, l_ in zip(pyr[1:], lv):
+        assert torch.equal(p_.view(-1), l_.view(-1))
 
 
 def test_corr_pyramid_generic_width(sb):
@@ -807,6 +809,26 @@ def test_composite_vs_oracle(sb, hw, with_occ):
     assert_bits_equal(host(r["blend_image"]), ref["blend_image"], "blend_image")
 
 
+def test_composite_w6_reference_block(sb):
+    """W6 on the GPU against the reference's own compositing block (inputs + outputs captured inside its
+    test_out_forward, tests/golden/composite_w6.npz): bit-exact values, masks and uint8 blend."""
+    g = golden("composite_w6")
+    # :317 as the product path does it — fused into the flow warp's epilogue (mul_mask); here the multiply alone
+    fw_in = cu(g["warp_out"]) * cu(g["flow_mask"])
+    assert_bits_equal(host(fw_in).view(np.uint32), g["final_warp_in"].view(np.uint32), "final_warp * flow_mask")
+    r = sb.composite_test_out(cu(g["homo_output"]), cu(g["homo_output2"]), fw_in, cu(g["occlusion_mask"]))
+    assert_bits_equal(host(r["final_warp_output"][:, 0:3].contiguous()).view(np.uint32), g["out_final_warp"].view(np.uint32),
+                      "final_warp")
+    for k in ("output1", "output2", "mask1", "mask2"):
+        a, b = host(r[k].contiguous()), g["out_" + k]
+        assert_bits_equal(np.isnan(a), np.isnan(b), k + " NaN pattern")
+        assert_bits_equal(a.view(np.uint32)[~np.isnan(a)], b.view(np.uint32)[~np.isnan(b)], k)
+    assert r["blend_image"].dtype == torch.uint8
+    assert_bits_equal(host(r["blend_image"]), g["out_blend_image"], "blend_image (uint8)")
+    assert_bits_equal(host(r["mask1"]) > 0.5, g["out_mask1"] > 0.5, "mask1 thresholded")
+    assert_bits_equal(host(r["mask2"]) > 0.5, g["out_mask2"] > 0.5, "mask2 thresholded")
+
+
 def test_build_model_golden(sb):
     c = cases.build_model_small()
     g = golden("build_model")
@@ -818,6 +840,7 @@ def test_build_model_golden(sb):
 
 
 def test_tps_mix_golden(sb):
+    """W8 against the reference's own tps_H_warp (tps_pipline.py:138-170 executed as written)."""
     c = cases.tps_mix_small()
     g = golden("tps_mix")
     check_inputs(g, *c.values())

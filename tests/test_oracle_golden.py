@@ -208,7 +208,30 @@ def test_morph(name):
     assert set(np.unique(out)) <= {0.0, 1.0}
 
 
-# ---------------------------------------------------------------- W7 / W8
+# ---------------------------------------------------------------- W6 / W7 / W8
+def test_composite_w6_reference_block():
+    """W6: the oracle's fused compositing against the inputs and outputs of the reference's OWN block
+    (flowHomoAdpater.py:317,339-360), captured inside a run of its test_out_forward (make_golden.py spies on
+    transformer / warp / preprocess_occlusion_mask).  Per-pixel arithmetic, so the stored pixel subset
+    (cases.W6_SAMPLE) is a complete vector.  Bit-exact, including the uint8 blend and the 0/0 pixels."""
+    g = golden("composite_w6")
+    fw_in = g["warp_out"] * g["flow_mask"]                                   # :317 (one fp32 multiply)
+    assert_bits_equal(fw_in.view(np.uint32), g["final_warp_in"].view(np.uint32), "final_warp * flow_mask")
+    r = so.composite_test_out(g["homo_output"], g["homo_output2"], fw_in, g["occlusion_mask"])
+    assert_bits_equal(r["final_warp_output"][:, 0:3].view(np.uint32), g["out_final_warp"].view(np.uint32), "final_warp")
+    for k in ("output1", "output2", "mask1", "mask2"):
+        a, b = np.ascontiguousarray(r[k]), g["out_" + k]
+        nan_a, nan_b = np.isnan(a), np.isnan(b)
+        assert_bits_equal(nan_a, nan_b, k + " NaN pattern")
+        assert_bits_equal(a.view(np.uint32)[~nan_a], b.view(np.uint32)[~nan_b], k)
+    assert r["blend_image"].dtype == np.uint8
+    assert_bits_equal(r["blend_image"], g["out_blend_image"], "blend_image (uint8)")
+    # the case exercises every region: overlap, img1 only, img2 only, nothing, occluded
+    m1, m2 = g["out_mask1"][0, 0] > 0.5, g["out_mask2"][0, 0] > 0.5
+    for region in (m1 & m2, m1 & ~m2, ~m1 & m2, ~m1 & ~m2, g["occlusion_mask"][0, 0] < 0.5):
+        assert region.sum() > 20
+
+
 def test_build_model():
     c = cases.build_model_small()
     g = golden("build_model")
@@ -219,6 +242,8 @@ def test_build_model():
 
 
 def test_tps_mix():
+    """W8 against the reference's own tps_H_warp (core/inference/tps_pipline.py:138-170 executed as written,
+    stages upstream of :138 stubbed — see make_golden.py)."""
     c = cases.tps_mix_small()
     g = golden("tps_mix")
     check_inputs(g, *c.values())

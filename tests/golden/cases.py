@@ -321,6 +321,28 @@ def adapter_test_out():
     return dict(image1=im1.contiguous(), image2=im2.contiguous(), offsets=offsets, flows=flows)
 
 
+def demo1_pair():
+    """BASELINE config 1: the reference's demo/demo1 pair (tests/golden/demo1/input{1,2}.jpg, copies of the
+    reference's fixture files), decoded as out.py:129-146 does (cv2 BGR -> RGB, float 0..255, [1,3,512,512]),
+    with the SURVEY 8(d) stand-ins for the networks: 4-point offsets N(0, 20^2) px, smooth residual flows
+    N(0, 2^2) at 1/8 resolution upsampled x8, a 13x13 TPS mesh with N(0, 0.02^2) targets."""
+    import os
+    import cv2
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "demo1")
+    ims = []
+    for name in ("input1.jpg", "input2.jpg"):
+        im = cv2.cvtColor(cv2.imread(os.path.join(here, name)).astype("uint8"), cv2.COLOR_BGR2RGB)
+        ims.append(torch.from_numpy(np.array(im).astype(np.uint8)[..., :3]).permute(2, 0, 1).float().unsqueeze(0).contiguous())
+    g = _g(95)
+    offsets = torch.randn(1, 4, 2, generator=g) * 20.0
+    flows = [_smooth_flow(g, 1, 512, 2.0), _smooth_flow(g, 1, 512, 2.0)]
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, 13), torch.linspace(-1, 1, 13), indexing="ij")
+    src = torch.stack([xs, ys], -1).reshape(1, -1, 2)
+    tgt = src + 0.02 * torch.randn(1, 169, 2, generator=g)
+    return dict(image1=ims[0], image2=ims[1], offsets=offsets, flows=flows, tps_source=src, tps_target=tgt)
+
+
+DEMO1_SAMPLE = (slice(2, None, 5), slice(1, None, 5))
 ADAPTER_SAMPLE = (slice(None, None, 3), slice(None, None, 3))
 # pixels of the test_out canvas whose compositing inputs AND outputs are stored (tests/golden/composite_w6.npz)
 W6_SAMPLE = (slice(1, None, 4), slice(2, None, 4))

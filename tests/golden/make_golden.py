@@ -124,7 +124,8 @@ def main():
         out = MemoryDecoder.encode_flow_token(None, c["cost_maps"], c["coords"])
         extra = {}
         if name == "lookup_small":
-            extra["out_r2"] = MemoryDecoder.encode_flow_token(None, c["cost_maps"], c["coords"], r=2).numpy()
+            for rr in (0, 1, 2, 7):      # radii of the non-default branches (decoder.py:295-315); r = 0: the centre only
+                extra[f"out_r{rr}"] = MemoryDecoder.encode_flow_token(None, c["cost_maps"], c["coords"], r=rr).contiguous().numpy()
             # C3p convention (common.py:245-248): centroid / 2**i + delta on pooled maps
             pyr = [c["cost_maps"]]
             for _ in range(2):
@@ -358,6 +359,59 @@ def main():
     arrays["H"] = od["H"].numpy()
     arrays["I_mat"] = od["I_mat"].numpy()
     save("adapter_test_out", cases.checksum(c["image1"], c["image2"], c["offsets"], *c["flows"]), **arrays)
+
+    # ---------------------------------------------------------------- BASELINE config 1: the reference's
+    # demo/demo1 pair through the path on the CPU (out.py:129-146 loading; stub networks per SURVEY 8(d)).
+    # Kernel-level vectors (the thetas the reference computed + a pixel subset of every intermediate) so
+    # that each CUDA kernel can be checked bit for bit on real image content, plus the adapter's out_dict.
+    c = cases.demo1_pair()
+    ad = ref_ad.FlowHomoAdpater(cases.StubHomo(c["offsets"]), cases.StubFlow(c["flows"]), cases.adapter_cfg())
+    ad.eval()
+    calls = dict(transformer=[], warp=[], morph=[], occ=[])
+    orig = (ref_ad.torch_homo_transform.transformer, ref_ad.warp, ref_ad.preprocess_occlusion_mask, ref_ad.compute_occlusion)
+
+    def _rec(key, fn):
+        def wrapped(*a, **k):
+            r = fn(*a, **k)
+            calls[key].append((a, k, r.clone()))
+            return r
+        return wrapped
+
+    ref_ad.torch_homo_transform.transformer = _rec("transformer", orig[0])
+    ref_ad.warp = _rec("warp", orig[1])
+    ref_ad.preprocess_occlusion_mask = _rec("morph", orig[2])
+    ref_ad.compute_occlusion = _rec("occ", orig[3])
+    try:
+        od = ad.test_out_forward(c["image1"], c["image2"])
+    finally:
+        (ref_ad.torch_homo_transform.transformer, ref_ad.warp, ref_ad.preprocess_occlusion_mask,
+         ref_ad.compute_occlusion) = orig
+    assert [len(calls[k]) for k in ("transformer", "warp", "morph", "occ")] == [5, 1, 2, 1]
+    dy, dx = cases.DEMO1_SAMPLE
+    sub = lambda t: t[..., dy, dx].contiguous().numpy()
+    bits = lambda t: np.packbits(t.numpy() > 0.5)
+    tr = calls["transformer"]
+    arrays = dict(pixels_checksum=np.float64(cases.checksum(c["image1"], c["image2"])),
+                  canvas=np.array([od["width_min"], od["height_min"], od["out_height"], od["out_width"]]),
+                  theta_H512=tr[0][0][1].numpy(), theta_I=tr[1][0][1].numpy(), theta_H=tr[2][0][1].numpy(),
+                  output_H512_sample=sub(tr[0][2]), homo_output_sample=sub(tr[1][2]), homo_output2_sample=sub(tr[2][2]),
+                  residual_flow_output_sample=sub(tr[3][2]), warp_out_sample=sub(calls["warp"][0][2]),
+                  occ_raw_sample=sub(calls["occ"][0][2]), occ_raw_bits=bits(calls["occ"][0][2]),
+                  origin_occlusion_bits=bits(calls["morph"][0][2]), occ_canvas_sample=sub(tr[4][2]),
+                  occ_canvas_bits=bits(tr[4][2]), occlusion_bits=bits(calls["morph"][1][2]),
+                  warp_input2_mask_bits=bits(od["warp_input2_mask"]), H=od["H"].numpy())
+    # at 512^2 resize_flow (:241) is the identity: the flows compute_occlusion saw ARE the case's flows
+    assert torch.equal(calls["occ"][0][1]["flow_ij"], c["flows"][0]) and torch.equal(calls["occ"][0][1]["flow_ji"], c["flows"][1])
+    for k in ("H_warp", "final_warp", "output1", "output2", "mask1", "mask2", "H_warp_mask", "blend_image"):
+        arrays["out_" + k + "_sample"] = sub(od[k])
+    arrays["mask1_bits"], arrays["mask2_bits"] = bits(od["mask1"]), bits(od["mask2"])
+    # W3 on real pixels: the UDIS TPS warp of (image1 | ones) with the 13x13 mesh
+    U = torch.cat((c["image1"], torch.ones_like(c["image1"])), 1)
+    tps_out, rec = capture_gather_indices(ref_tps.transformer, U, c["tps_source"], c["tps_target"], (512, 512))
+    arrays["tps_out_sample"] = sub(tps_out)
+    arrays["tps_idx_sample"] = decode_indices(rec, 1, 512, 512, 512, 512)[..., dy, dx]
+    save("demo1_pair", cases.checksum(c["image1"], c["image2"], c["offsets"], *c["flows"], c["tps_source"], c["tps_target"]),
+         **arrays)
 
 
 if __name__ == "__main__":

@@ -296,6 +296,48 @@ def test_lookup_full_size_vs_oracle(sb):
     assert torch.equal(out, sb.encode_flow_token(maps, coords))
 
 
+def test_pyramid_lookup_on_fused_levels_64(sb):
+    """C3p on the levels the cost-volume kernel's fused epilogue wrote (64x64 -> 32, 16, 8): every level's
+    81 taps bit-exact against the oracle's lookup of the SAME level with the centre scaled by 2^-l
+    (common.py:245-248 convention); level-major channel order."""
+    g = torch.Generator().manual_seed(31)
+    f1, f2 = torch.randn(1, 128, 64, 64, generator=g), torch.randn(1, 128, 64, 64, generator=g)
+    vol, lv = sb.corr.corr(cu(f1), cu(f2), pyramid_levels=3)
+    pyr = [vol.view(4096, 1, 64, 64), lv[0], lv[1], lv[2]]
+    assert [tuple(p.shape[-2:]) for p in pyr] == [(64, 64), (32, 32), (16, 16), (8, 8)]
+    coords = cases.coords_grid(1, 64, 64) + torch.randn(1, 2, 64, 64, generator=g) * 3.0
+    coords[0, :, 0, :] = cases.coords_grid(1, 64, 64)[0, :, 0, :]           # exact integers
+    coords[0, :, 1, :4] = -40.0                                              # outside every level
+    coords[0, :, 2, :4] = 63.0
+    out = sb.encode_flow_token_pyramid(pyr, cu(coords))
+    assert out.shape == (1, 4 * 81, 64, 64) and tuple(out.stride()) == (4 * 81 * 4096, 1, 64 * 4 * 81, 4 * 81)
+    got = host(out.contiguous())
+    for l, pm in enumerate(pyr):
+        ref = so.encode_flow_token(host(pm), coords.numpy(), coord_scale=1.0 / (1 << l))
+        assert_bits_equal(got[:, l * 81:(l + 1) * 81], np.ascontiguousarray(ref), f"pyramid level {l}")
+    ref_all = so.encode_flow_token_pyramid([host(pm) for pm in pyr], coords.numpy())
+    assert_bits_equal(got, np.ascontiguousarray(ref_all), "all levels")
+
+
+@pytest.mark.parametrize("r", [0, 1, 2, 3, 5, 7])
+def test_lookup_other_radii(sb, r):
+    """decoder.py:295-315 calls encode_flow_token with radii other than 4 in non-default branches
+    (r = 0 is the single centre sample): generic kernel, bit-exact against the oracle."""
+    c = cases.lookup_small()
+    out = sb.encode_flow_token(cu(c["cost_maps"]), cu(c["coords"]), r=r)
+    side = 2 * r + 1
+    assert out.shape == (2, side * side, 3, 5)
+    ref = so.encode_flow_token(c["cost_maps"].numpy(), c["coords"].numpy(), r=r)
+    assert_bits_equal(host(out.contiguous()), np.ascontiguousarray(ref), f"r={r}")
+    g = golden("lookup_small")
+    if f"out_r{r}" in g.files:
+        assert_bits_equal(host(out.contiguous()), g[f"out_r{r}"], f"r={r} vs the reference's own output")
+    c64 = cases.lookup_64()
+    out = sb.encode_flow_token(cu(c64["cost_maps"]), cu(c64["coords"]), r=r)
+    ref = so.encode_flow_token(c64["cost_maps"].numpy(), c64["coords"].numpy(), r=r)
+    assert_bits_equal(host(out.contiguous()), np.ascontiguousarray(ref), f"64x64 maps, r={r}")
+
+
 def test_bilinear_sampler(sb):
     g = golden("bilinear_sampler")
     out, m = sb.bilinear_sampler(cu(g["img"]), cu(g["pts"]), mask=True)

@@ -53,7 +53,8 @@ def test_lookup(name):
     assert_bits_equal(out, g["out"], "lookup")
     assert tuple(g["out_strides"]) == tuple(s // 4 for s in out.strides)
     if name == "lookup_small":
-        assert_bits_equal(so.encode_flow_token(c["cost_maps"].numpy(), c["coords"].numpy(), r=2), g["out_r2"], "r=2")
+        for rr in (0, 1, 2, 7):
+            assert_bits_equal(so.encode_flow_token(c["cost_maps"].numpy(), c["coords"].numpy(), r=rr), g[f"out_r{rr}"], f"r={rr}")
         pyr = [c["cost_maps"].numpy()]
         for _ in range(2):
             pyr.append(so.avg_pool2x2(pyr[-1]))

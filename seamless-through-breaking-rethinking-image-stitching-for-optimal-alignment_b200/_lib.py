@@ -115,6 +115,18 @@ def dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError(
             f"{name}: tensor is on {t.device}; stitch_b200 runs on B200 GPUs only (no CPU fallback)")
+    if t.requires_grad and torch.is_grad_enabled():
+        # The kernels are forward-only: they are reached through raw pointers, so autograd would silently see a
+        # detached result (a loss without grad_fn, weights that never train).  Inference only — say so loudly.
+        raise RuntimeError(
+            f"{name}: requires_grad tensor with autograd enabled; stitch_b200 kernels are inference-only "
+            "(no backward pass): call under torch.no_grad() / model.eval(), or detach the input")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the calling thread's current device and stream (as nn.DataParallel's replica threads
+        # set them); a tensor that lives elsewhere would be dereferenced on the wrong GPU
+        raise RuntimeError(
+            f"{name}: tensor is on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+            f"wrap the call in `with torch.cuda.device({t.device.index}):`")
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()

@@ -10,6 +10,10 @@ path: they are passed in exactly like in the reference and called through
 homography / flow warps, occlusion, morphology, compositing — runs through the
 sm_100a kernels of this package (geometry helpers of row G1 stay in torch).
 
+INFERENCE ONLY: the kernels have no backward pass.  ``forward(type="train")`` raises while autograd is
+enabled, and any kernel input that requires grad raises (``_lib.dev_f32``) instead of returning a silently
+detached result.
+
 Only the branches the shipped configs select are implemented
 (``use_forward=False``, ``use_combine_h_flow=False``,
 ``test_not_use_combine_h_flow=True``); the reference's other branches are dead or
@@ -66,6 +70,11 @@ class FlowHomoAdpater(nn.Module):
         if type == "test_out":
             return self.test_out_forward(input1_tensor, input2_tensor, pad_mode=pad_mode,
                                          preprocess_callback=preprocess_callback)
+        if type == "train" and torch.is_grad_enabled():
+            # the reference backpropagates through DLT, both warps and the cost volume here; these kernels have
+            # no backward pass, so a training step would silently not train
+            raise NotImplementedError("FlowHomoAdpater(type='train') with autograd enabled: stitch_b200 is "
+                                      "inference-only; use type='test_eval' / 'test_out' under torch.no_grad()")
         if type in ("train", "test_eval"):
             return self.train_eval_foward(input1_tensor, input2_tensor)
         raise NotImplementedError(type)

@@ -73,9 +73,11 @@ def attention(fmap, to_qk_weight, heads: int = 1, scale: float | None = None, dt
         _lib.check(lib.sb_attn_softmax_tokens(_lib.ptr(tq), _lib.ptr(tk), _lib.ptr(attn), _lib.ptr(stats), b * heads,
                                               q.shape[1], n, n, _lib.stream_ptr()), "sb_attn_softmax_tokens")
         return attn.view(b, heads, n, n)
-    sim = corr_mod.corr(q, k).view(b * heads, n, n)          # bf16 x bf16 -> fp32 on the tensor cores
-    softmax_rows_(sim, to_tf32=True)
-    return sim.view(b, heads, n, n)
+    # token counts that are not a multiple of 4 (e.g. 65 x 67 maps): the contraction still runs on the tensor
+    # cores (corr() pads the row pitch for the TMA and returns a strided view); the row softmax of that ragged,
+    # pitched matrix is library code (torch), like the 1x1 convolutions
+    sim = corr_mod.corr(q, k).reshape(b * heads, n, n)       # bf16 x bf16 -> fp32 on the tensor cores
+    return torch.softmax(sim, dim=-1).view(b, heads, n, n)
 
 
 def attn_matmul_v(attn, v, residual=None, gamma=None):
@@ -107,6 +109,12 @@ def attn_matmul_v(attn, v, residual=None, gamma=None):
         raise ValueError(f"attn_matmul_v: v {tuple(vv.shape)} does not match attn {tuple(a.shape)}")
     res = _lib.dev_f32(residual, "residual") if residual is not None else None
     gm = _lib.dev_f32(gamma, "gamma") if gamma is not None else None
+    if nk % 4:
+        # ragged key count (the TMA needs 16-byte row strides): library GEMM on the GPU, same formula
+        out = torch.bmm(vv, a.transpose(1, 2))
+        if gm is not None:
+            out = gm * out
+        return out if res is None else res + out
     out = torch.empty((bh, d, nq), dtype=torch.float32, device=a.device)
     _lib.check(lib.sb_attn_aggregate(_lib.ptr(a), _lib.ptr(vv), _lib.ptr(res), _lib.ptr(gm), _lib.ptr(out),
                                      bh, nq, nk, d, _lib.stream_ptr()), "sb_attn_aggregate")
@@ -143,13 +151,29 @@ def aggregate_forward(self, attn, fmap):
                      None if self.project is None else self.project.weight, self.heads)
 
 
+class RelPosEmb(nn.Module):
+    """State of the reference's ``RelPosEmb`` (gma.py:6-18): two embeddings and an index buffer.  The
+    reference's ``Attention.forward`` never calls it (gma.py:54-76), so it has no forward here either; it
+    exists so that ``Attention.state_dict()`` has the reference's keys (``pos_emb.rel_height.weight``,
+    ``pos_emb.rel_width.weight``, ``pos_emb.rel_ind``) and its checkpoints load with ``strict=True``
+    (evaluate.py:123, out.py:75,85)."""
+
+    def __init__(self, max_pos_size, dim_head):
+        super().__init__()
+        self.rel_height = nn.Embedding(2 * max_pos_size - 1, dim_head)
+        self.rel_width = nn.Embedding(2 * max_pos_size - 1, dim_head)
+        deltas = torch.arange(max_pos_size).view(1, -1) - torch.arange(max_pos_size).view(-1, 1)
+        self.register_buffer("rel_ind", deltas + max_pos_size - 1)
+
+
 class Attention(nn.Module):
-    """Same constructor / parameters as the reference's ``Attention`` (gma.py:35-52)."""
+    """Same constructor, parameters and state_dict keys as the reference's ``Attention`` (gma.py:35-52)."""
 
     def __init__(self, *, args=None, dim, max_pos_size=100, heads=4, dim_head=128, attn_dtype=torch.float32):
         super().__init__()
         self.args, self.heads, self.scale = args, heads, dim_head ** -0.5
         self.to_qk = nn.Conv2d(dim, heads * dim_head * 2, 1, bias=False)
+        self.pos_emb = RelPosEmb(max_pos_size, dim_head)
         self.attn_dtype = attn_dtype
 
     def forward(self, fmap):

@@ -1,7 +1,11 @@
 """patch_reference() — drop the B200 kernels in behind the reference's own call
 surface by assigning this package's functions over the reference modules'
 attributes (SURVEY §8b lists the call sites). The reference must already be
-importable (``sys.path`` containing its root and ``core/``)."""
+importable (``sys.path`` containing its root and ``core/``).
+
+INFERENCE ONLY.  The kernels have no backward pass: run the patched reference the way its own
+``evaluate.py`` / ``out.py`` do — ``model.eval()`` under ``torch.no_grad()``.  With autograd enabled any
+patched function that receives a tensor requiring grad raises (it does not return a detached result)."""
 from __future__ import annotations
 
 import importlib
@@ -44,7 +48,9 @@ def patch_reference(verbose: bool = False):
     _set("core.FlowFormer.PerCostFormer3.gma", "forward", gma.attention_forward, cls="Attention")
     _set("core.FlowFormer.PerCostFormer3.gma", "forward", gma.aggregate_forward, cls="Aggregate")
     _set("core.UDIS2.Homography.network", "CCL", udis2_homography.udis2_network_ccl, cls="UDIS2Network")
-    # tps_method="kornia" branch (tps_pipline.py:364-381 imports these two names at call time)
+    # tps_method="kornia" branch (tps_pipline.py:364-381 imports the name at call time).  Only the dense warp is
+    # a kernel; `get_tps_transform` stays what the reference binds it to (kornia's own solve, kornia_tps.py:1):
+    # replacing it with the pinverse variant the reference defines but never calls would change the numerics
+    # of an often ill-conditioned system.
     _set("core.inference.tps_methods.kornia_tps", "warp_image_tps", kornia_tps.warp_image_tps)
-    _set("core.inference.tps_methods.kornia_tps", "get_tps_transform", kornia_tps.get_tps_transform)
     return done

@@ -21,3 +21,14 @@ def golden(name):
 @pytest.fixture(scope="session")
 def load_golden():
     return golden
+
+
+@pytest.fixture(autouse=True)
+def _inference_mode_like_the_reference():
+    """The reference evaluates under @torch.no_grad() (evaluate.py:22,111; out.py); the kernels are
+    inference-only and refuse tensors that require grad while autograd is enabled."""
+    import torch
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    yield
+    torch.set_grad_enabled(prev)

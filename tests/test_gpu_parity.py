@@ -606,6 +606,30 @@ def test_gma_full_size_vs_torch(sb):
 
 
 # ===================================================================== N3 (next row 3)
+def test_gma_ragged_token_count_and_autograd_guard(sb):
+    """Token maps whose size is not a multiple of 4 (the reference handles e.g. 65 x 67): the contraction runs
+    on the tcgen05 kernel with a padded pitch, softmax / aggregate on library code; and a requires_grad input
+    with autograd enabled is refused instead of silently detached."""
+    g = torch.Generator().manual_seed(77)
+    h, w = 5, 7
+    fmap, motion = torch.randn(2, 128, h, w, generator=g), torch.randn(2, 128, h, w, generator=g)
+    w_qk, w_v = torch.randn(256, 128, 1, 1, generator=g) * 0.1, torch.randn(128, 128, 1, 1, generator=g) * 0.1
+    gamma = torch.tensor([0.7])
+    attn = sb.gma.attention(cu(fmap), cu(w_qk), heads=1)
+    ref_attn = so.gma_attention(fmap.numpy(), w_qk.numpy(), heads=1)
+    assert attn.shape == (2, 1, h * w, h * w)
+    assert max_abs(host(attn), ref_attn) <= 3e-2 * float(ref_attn.max())
+    out = sb.gma.aggregate(attn, cu(motion), cu(w_v), cu(gamma))
+    ref_out = so.gma_aggregate(host(attn), motion.numpy(), w_v.numpy(), gamma.numpy())
+    assert max_abs(host(out), ref_out) <= 1e-2 * float(np.abs(ref_out).max())
+    with torch.enable_grad():
+        x = cu(fmap).requires_grad_(True)
+        with pytest.raises(RuntimeError, match="inference-only"):
+            sb.corr.corr(x, x)
+        with pytest.raises(RuntimeError, match="inference-only"):
+            sb.warp(x[:, :6], cu(torch.zeros(2, 2, h, w)))
+
+
 def test_gemm_nt_tf32_vs_fp64(sb):
     gen = torch.Generator(device="cuda").manual_seed(81)
     for bh, m, n, k in ((2, 256, 128, 64), (3, 200, 136, 100), (1, 1024, 1024, 1024)):
@@ -969,6 +993,54 @@ def test_hot_path_step_small(sb):
                              return_overlap=True)
     assert_bits_equal(host(out["final_warp_output"]), ref_fw, "final_warp_output")
     assert_bits_equal(host(out["overlap"]), ref_ov, "overlap")
+
+
+def test_config3_batch64_volume_and_lookup_indexing(sb):
+    """BASELINE config 3 (batch 64 per GPU): a 4 GiB volume per direction — byte offsets beyond 2^31 and 2^32,
+    262144 cost maps.  Cost volume (+ fused pyramid) and lookup are checked on batches either side of the
+    2 GiB / 4 GiB boundaries; the full step then runs at batch 64."""
+    b = 64
+    g = torch.Generator(device="cuda").manual_seed(64)
+    f1 = torch.randn(b, 256, 64, 64, device="cuda", generator=g)
+    f2 = torch.randn(b, 256, 64, 64, device="cuda", generator=g)
+    vol, lv = sb.corr.corr(f1, f2, pyramid_levels=3)
+    assert vol.numel() * 4 == 4 << 30
+    v = vol.view(b, 4096, 4096)
+    for bi in (0, 31, 32, 33, 63):
+        ref = torch.bmm(f1[bi:bi + 1].bfloat16().float().view(1, 256, 4096).transpose(1, 2),
+                        f2[bi:bi + 1].bfloat16().float().view(1, 256, 4096))[0]
+        scale = ref.abs().max().item()
+        assert (v[bi] - ref).abs().max().item() <= 5e-5 * scale, bi
+        # fused pyramid of the same batch == chained pooling of the volume the kernel wrote
+        cm = v[bi].view(4096, 1, 64, 64)
+        l1 = torch.nn.functional.avg_pool2d(cm, 2, stride=2)
+        assert (lv[0].view(b, 4096, 1, 32, 32)[bi] - l1).abs().max().item() <= 1e-5 * scale, bi
+        l3 = torch.nn.functional.avg_pool2d(torch.nn.functional.avg_pool2d(l1, 2, stride=2), 2, stride=2)
+        assert (lv[2].view(b, 4096, 1, 8, 8)[bi] - l3).abs().max().item() <= 1e-5 * scale, bi
+        del ref, l1, l3
+    coords = sb.lookup.coords_grid(b, 64, 64, device="cuda") + torch.randn(b, 2, 64, 64, device="cuda", generator=g) * 3.0
+    maps = vol.view(b * 4096, 1, 64, 64)
+    out = sb.encode_flow_token(maps, coords)
+    assert out.shape == (b, 81, 64, 64)
+    for bi in (0, 31, 32, 63):
+        ref = so.encode_flow_token(host(maps[bi * 4096:(bi + 1) * 4096]), host(coords[bi:bi + 1]))
+        assert_bits_equal(host(out[bi:bi + 1].contiguous()), np.ascontiguousarray(ref), f"lookup, batch {bi}")
+    del vol, lv, out, maps, v
+    torch.cuda.empty_cache()
+    # the whole step at batch 64 equals four steps at batch 16 on the same pairs (pairs are independent)
+    from stitch_b200.pipeline import HotPath, make_pair_batch
+    pb = make_pair_batch(0, b, size=512, iters=1).map(lambda t: t.cuda())
+    hp = HotPath(size=512, iters=1, pyramid=True)
+    big = hp.step(pb)
+    torch.cuda.synchronize()
+    for s0 in (0, 48):
+        part = pb.map(lambda t: t[s0:s0 + 16].contiguous() if t.shape[0] == b else t[:, s0:s0 + 16].contiguous())
+        small = hp.step(part)
+        for k in ("final_warp_output", "overlap", "origin_occlusion_mask", "output_H", "cost_volume"):
+            assert torch.equal(big[k][s0:s0 + 16], small[k]), (k, s0)
+        assert torch.equal(big["cost_tokens"][0][s0:s0 + 16], small["cost_tokens"][0])
+        assert torch.equal(big["cost_pyramid_back"][2].view(b, -1)[s0:s0 + 16], small["cost_pyramid_back"][2].view(16, -1))
+        del small
 
 
 # ===================================================================== G1 fused geometry / ones fusion

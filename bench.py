@@ -3,12 +3,18 @@
 (cost volume + lookup + warp), BASELINE.json's metric.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own functions on the host CPU
+    python bench.py --batch 64 ...                           # BASELINE config 3 (64 pairs per GPU)
 
-One *step* = one batch of 16 synthetic UDIS-D-shaped pairs per GPU through the op
+One *step* = one batch of 16 (``--batch``) synthetic UDIS-D-shaped pairs per GPU through the op
 list of the reference's ``train_eval_foward`` (2 x cost volume (+pyramid), 24 x
 lookup, 2 x homography warp, occlusion, flow warp).
 Prints ONE JSON line (rank 0).
+
+CPU legs: ``--impl reference`` and the ``cpu_baseline`` key time the UNMODIFIED reference functions
+(baseline/_ref, copied from /root/reference by ``__graft_entry__.build()``; git-ignored, travels with the gpurun
+snapshot) in a ``CUDA_VISIBLE_DEVICES=""`` subprocess on all host threads, on the same seeded batch
+(``kind: "reference"``).  Where that copy is absent the oracle port is timed instead (``kind: "port"``).
 """
 from __future__ import annotations
 
@@ -31,9 +37,20 @@ SIZE = 512
 ITERS = 12
 
 
-def workload_name(n_gpus):
-    return (f"synthetic UDIS-D 512x512 pairs, batch {BATCH_PER_GPU} per GPU, cost volume (+pyramid) + "
+def workload_name(n_gpus, batch=BATCH_PER_GPU):
+    return (f"synthetic UDIS-D 512x512 pairs, batch {batch} per GPU, cost volume (+pyramid) + "
             f"24 lookups + 2 homography warps + occlusion + flow warp on {n_gpus}xB200")
+
+
+def workload_config(n_gpus, batch):
+    """The workload description — IDENTICAL for our arm and the reference arm (same keys, same values)."""
+    from stitch_b200.pipeline import algorithmic_work
+    work = algorithmic_work(batch, SIZE, ITERS, 256, pyramid=True)
+    return {"workload": workload_name(n_gpus, batch), "global_batch": batch * n_gpus, "batch_per_gpu": batch,
+            "image_size": SIZE, "lookup_iters": ITERS, "feature_channels": 256,
+            "parallelism": f"pairs sharded x{n_gpus}, no data-path collective",
+            "l2": "per-step working set (2 volumes of batch x 64 MiB) >> 126 MB L2 (and >> the host LLC), no explicit flush",
+            "algorithmic_bytes_per_step": work["bytes"], "algorithmic_flops_per_step": work["flops"]}
 
 
 # --------------------------------------------------------------------- clocks
@@ -137,29 +154,80 @@ def cpu_model() -> str:
     return "unknown"
 
 
+REF_COPY = os.environ.get("STITCH_REF_COPY") or os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_cpu_steps(batch, steps, warmup, max_seconds):
+    """The reference's own functions (baseline/_ref) on all host threads in a CUDA_VISIBLE_DEVICES="" subprocess.
+    Returns the runner's report (dict) or None when the reference copy is absent / the run failed."""
+    if not os.path.isdir(os.path.join(REF_COPY, "core")):
+        return None
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        env[var] = str(os.cpu_count())             # torchrun exports OMP_NUM_THREADS=1
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "run_reference_cpu.py"), "--pairs", str(batch), "--size", str(SIZE),
+           "--iters", str(ITERS), "--steps", str(steps), "--warmup", str(warmup), "--max-seconds", str(max_seconds)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=max(600.0, 4 * max_seconds))
+    except subprocess.TimeoutExpired:
+        return None
+    if r.returncode != 0:
+        sys.stderr.write("reference CPU run failed:\n" + r.stderr[-2000:] + "\n")
+        return None
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    return None
+
+
+def cpu_baseline_entry(batch, steps, warmup, max_seconds, port_seconds):
+    """cpu_baseline object: the reference itself when its copy is present (kind "reference"), the oracle port
+    beside it (and alone, kind "port", where the copy is absent)."""
+    rep = reference_cpu_steps(batch, steps, warmup, max_seconds)
+    port_v, port_done = cpu_pairs_per_s(2, port_seconds)
+    port = {"value": port_v, "unit": UNIT, "kind": "port", "sample": f"{port_done} pairs, oracle port (numpy BLAS + OpenMP C)"}
+    if rep is None:
+        return dict(port, cores=os.cpu_count(), cpu_model=cpu_model()), None
+    secs = rep["step_seconds"]
+    value = rep["pairs_per_step"] / statistics.mean(secs)
+    entry = {"value": value, "unit": UNIT, "cores": rep["threads"], "kind": "reference", "cpu_model": rep["cpu_model"],
+             "sample": (f"{len(secs)} steps of {rep['pairs_per_step']} pairs (after {warmup} warm-up) through the reference's own "
+                        "functions (baseline/_ref: MemoryEncoder.corr, MemoryDecoder.encode_flow_token, "
+                        "FlowHomoAdpater.train_eval_foward with stub networks), CUDA_VISIBLE_DEVICES='' subprocess, "
+                        "torch.set_num_threads(os.cpu_count())"),
+             "best_step_value": rep["pairs_per_step"] / min(secs), "torch_parallel_info": rep["parallel_info"],
+             "oracle_port": port}
+    return entry, rep
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path. The reference is
-    pure Python and cannot travel to the GPU box (no /root/reference there), so the timed code is
-    the oracle port (cpu_baseline.kind = "port"). Rank 0 only; other ranks exit."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, same batch
+    and config keys as our arm. Rank 0 only; other ranks exit."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    sample_pairs = 2
-    per_step = []
-    cpu_pairs_per_s(sample_pairs, 0.0)  # warm
-    for i in range(args.warmup + args.steps):
-        v, _ = cpu_pairs_per_s(sample_pairs, 0.0)
-        if i >= args.warmup:
-            per_step.append(v)
-    value = statistics.mean(per_step)
-    cores = os.cpu_count()
+    batch = args.batch
+    # every step is one full batch (the same one our arm processes); the run is bounded to a few minutes
+    entry, rep = cpu_baseline_entry(batch, args.steps, args.warmup, max_seconds=240.0, port_seconds=0.0)
+    if rep is not None:
+        secs = rep["step_seconds"]
+        value, ms_per_step, steps_done = entry["value"], 1000.0 * statistics.mean(secs), len(secs)
+    else:
+        # no reference copy on this box: the oracle port, a bounded sample of 2 pairs per step
+        per_step = []
+        for i in range(args.warmup + args.steps):
+            v, _ = cpu_pairs_per_s(2, 0.0)
+            if i >= args.warmup:
+                per_step.append(v)
+        value = statistics.mean(per_step)
+        ms_per_step, steps_done = 1000.0 * batch / value, args.steps
+        entry = dict(entry, value=value, sample=f"2 pairs per step x {args.steps} steps, oracle port, all host threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sample_pairs / value,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus), "note": "CPU arm: each step is a bounded sample of "
-                   f"{sample_pairs} pairs of the same workload on the host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(),
-                         "sample": f"{sample_pairs} pairs per step x {args.steps} steps, all host threads (OpenMP + BLAS)"},
+        "config": workload_config(args.gpus, batch),
+        "steps_timed": steps_done,
+        "cpu_baseline": entry,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -187,7 +255,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().sb_device_check(), "sb_device_check")
 
-    B = BATCH_PER_GPU
+    B = args.batch
     # rank r owns pairs [r*B, (r+1)*B) of the global list (weak scaling, no data-path collective)
     # pinned host staging buffers (--wc: write-combined, filled once by the CPU, read by the device)
     pb_host = make_pair_batch(rank * B, B, size=SIZE, iters=ITERS).map(
@@ -306,7 +374,47 @@ def run_ours(args):
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = pairs_total / (t.item() / 1000.0)
+    e2e_ms = t.item()
     out = last_out()
+    h2d_peak_gbs = e2e_images = None
+    if args.graph:
+        # (a) what the host->device path can do on this box: the same pinned batch copied back to back on the two
+        #     copy streams the pipeline uses, nothing else running
+        dev_in = sp.slots[0]["dev_in"]
+        pairs = list(zip(dev_in.tensors(), pb_host.tensors()))
+        def h2d_once():
+            for st_, part in ((sp.s_in, pairs[0::2]), (sp.s_in2, pairs[1::2])):
+                st_.wait_stream(stream)
+                with torch.cuda.stream(st_):
+                    for d_, h_ in part:
+                        d_.copy_(h_, non_blocking=True)
+            stream.wait_stream(sp.s_in); stream.wait_stream(sp.s_in2)
+        h2d_once(); barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(5):
+            h2d_once()
+        c1.record(stream)
+        barrier()
+        h2d_peak_gbs = 5 * h2d / (c0.elapsed_time(c1) / 1000.0) / 1e9
+        # (b) SECONDARY figure, clearly labelled: only the two images cross the host boundary (what the reference's
+        #     evaluate.py:43 moves); features / flows / lookup centres stay device-resident stand-ins, as they are
+        #     produced on the device in the real product. Never a replacement for the all-from-host figure above.
+        sp.host_keys = ("image1", "image2")
+        run_e2e(2)
+        barrier()
+        c0.record(stream)
+        run_e2e(args.steps)
+        c1.record(stream)
+        barrier()
+        ti = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+        e2e_images = {"value": pairs_total / (ti.item() / 1000.0), "unit": UNIT,
+                      "h2d_bytes_per_step": sp.h2d_bytes(), "d2h_bytes_per_step": d2h,
+                      "note": "SECONDARY: only image1/image2 are uploaded each step (evaluate.py:43); the network "
+                              "stand-ins (features, flows, lookup centres) stay on the device"}
+        sp.host_keys = None
     # clocks were sampled from before the device-resident timed region to after the end-to-end one
     clocks = sampler.stop() if rank == 0 else None
 
@@ -340,22 +448,22 @@ def run_ours(args):
             pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, done = cpu_pairs_per_s(2, 12.0)
-            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "cpu_model": cpu_model(),
-                   "sample": f"{done} pairs of the same op list (oracle port: numpy BLAS + OpenMP C), all host threads"}
+            # bounded sample: 1 warm-up + 3 timed steps of the same batch through the reference itself (~15-25 s of
+            # CPU work at batch 16), the oracle port (12 s) beside it
+            cpu, _ = cpu_baseline_entry(B, 3, 1, max_seconds=60.0, port_seconds=12.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(world), "global_batch": B * world, "image_size": SIZE,
-                       "lookup_iters": ITERS, "submission": ("cuda-graph replay" if args.graph else "eager launches") +
-                       (", warp stage on a second stream (fork/join)" if args.overlap else ""),
-                       "parallelism": f"pairs sharded x{world}, no data-path collective",
-                       "l2": "per-step working set (2 x 1 GiB volumes) >> 126 MB L2, no explicit flush",
-                       "algorithmic_bytes_per_step": work["bytes"], "algorithmic_flops_per_step": work["flops"]},
+            "config": workload_config(world, B),
+            "submission": ("cuda-graph replay" if args.graph else "eager launches") +
+                          (", warp stage on a second stream (fork/join)" if args.overlap else ""),
             "roofline": {"bound": "hbm", "kernel": "corr_umma_kernel<true> (tcgen05 cost volume + fused pyramid)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": gemm_avg_ms,
+                         "traffic": traffic,
+                         "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture "
+                                           "of this kernel at this shape (profiles/corr_umma_traffic.json); not re-measured in this run",
+                         "peak_source": peak_src, "avg_launch_ms": gemm_avg_ms,
                          "launches_timed": len(gemm_ms), "algorithmic_bytes_per_launch": gemm_bytes,
                          "tensor_tflops": gemm_flops / (gemm_avg_ms / 1000.0) / 1e12,
                          "tensor_frac_of_sustained": (gemm_flops / (gemm_avg_ms / 1000.0) / 1e12) /
@@ -367,6 +475,11 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "wall_ms_per_step": wall_ms / args.steps,
+                    # the host->device copy bounds this figure: achieved GB/s of the timed region against the
+                    # same copies measured alone on this box
+                    "pcie_gbs": h2d * args.steps / (e2e_ms / 1000.0) / 1e9, "h2d_peak_gbs": h2d_peak_gbs,
+                    "pcie_frac": (h2d * args.steps / (e2e_ms / 1000.0) / 1e9 / h2d_peak_gbs) if h2d_peak_gbs else None,
+                    "images_only": e2e_images,
                     "how": ("double-buffered 3-stream pipeline (H2D | graph replay | D2H overlap)" if args.graph
                             else "serial H2D -> step -> D2H on one stream")},
             "gpu_launches": launches,
@@ -384,6 +497,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="pairs per GPU and step (16 = config 2, 64 = config 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="eager launches instead of replaying the step as one captured CUDA graph")

@@ -17,19 +17,40 @@ def _run(extra_env=None, *args):
     return subprocess.run([sys.executable, BENCH, *args], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
 
 
-def test_reference_arm_line():
-    r = _run(None, "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0")
+def _check_reference_line(r, batch, kind):
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "512x512 pairs/sec (cost volume+warp)" and d["unit"] == "pairs/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
-    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] / 1000.0 - 2) < 1e-6      # 2 pairs per step
+    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] / 1000.0 - batch) < 1e-6      # one batch per step
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] and cb["sample"]
+    assert cb["kind"] == kind and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["vs_baseline"] is None and d["gpu_launches"] == 0 and "workload" in d["config"]
+    assert d["vs_baseline"] is None and d["gpu_launches"] == 0
+    # the reference arm describes the SAME workload with the SAME config keys as our arm
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == json.loads(json.dumps(bench.workload_config(1, batch)))
+    return d
+
+
+def test_reference_arm_line_runs_the_reference_itself():
+    """With the reference copy present (baseline/_ref, made by build() where /root/reference exists) the CPU arm
+    times the reference's own functions: kind == "reference", torch's parallel info in the line."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "core")):
+        import pytest
+        pytest.skip("baseline/_ref absent (build() has not run where the reference tree exists)")
+    r = _run(None, "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0", "--batch", "2")
+    d = _check_reference_line(r, 2, "reference")
+    assert d["cpu_baseline"]["torch_parallel_info"] and d["cpu_baseline"]["oracle_port"]["kind"] == "port"
+
+
+def test_reference_arm_line_falls_back_to_the_port():
+    r = _run({"STITCH_REF_COPY": "/nonexistent"}, "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0",
+             "--batch", "2")
+    _check_reference_line(r, 2, "port")
 
 
 def test_reference_arm_other_ranks_do_no_work():

@@ -705,8 +705,8 @@ def test_next_rows_empty_and_bad_inputs(sb):
         sb.udis2_homography.CCL(z(1, 64, 8, 8), z(1, 64, 8, 9))
     with pytest.raises(RuntimeError, match="dim_head"):
         sb.gma.attn_matmul_v(z(1, 64, 64), z(1, 96, 64))
-    with pytest.raises(RuntimeError, match="multiple of 4"):
-        sb.gma.attn_matmul_v(z(1, 66, 66), z(1, 128, 66))
+    # a key count that is not a multiple of 4 is served by the library GEMM (the reference accepts any size)
+    assert tuple(sb.gma.attn_matmul_v(z(1, 66, 66), z(1, 128, 66)).shape) == (1, 128, 66)
 
 
 # ===================================================================== N2 (next row 2)

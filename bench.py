@@ -261,7 +261,8 @@ def run_ours(args):
     pb_host = make_pair_batch(rank * B, B, size=SIZE, iters=ITERS).map(
         (lambda t: _lib.pinned_like(t, write_combined=True)) if args.wc else (lambda t: t.pin_memory()))
     pb_dev = pb_host.map(lambda t: t.to(dev, non_blocking=True))
-    hp = HotPath(size=SIZE, iters=ITERS, pyramid=True, overlap=args.overlap, eval_outputs=not args.graph)
+    hp = HotPath(size=SIZE, iters=ITERS, pyramid=True, overlap=args.overlap, eval_outputs=not args.graph,
+                 lookup_subbatch=args.lookup_subbatch)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -457,7 +458,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world, B),
             "submission": ("cuda-graph replay" if args.graph else "eager launches") +
-                          (", warp stage on a second stream (fork/join)" if args.overlap else ""),
+                          (", warp stage on a second stream (fork/join)" if args.overlap else "") +
+                          (f", lookups per sub-batch of {args.lookup_subbatch} pairs" if args.lookup_subbatch else ""),
             "roofline": {"bound": "hbm", "kernel": "corr_umma_kernel<true> (tcgen05 cost volume + fused pyramid)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic,
@@ -503,6 +505,9 @@ def main():
                     help="eager launches instead of replaying the step as one captured CUDA graph")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="run the warp stage after the cost-volume stage instead of on a second stream")
+    ap.add_argument("--lookup-subbatch", type=int, default=0,
+                    help="run the 12 lookups of a direction per sub-batch of this many pairs (L2 residency experiment; "
+                         "0 = one lookup per iteration over the whole batch, as the decoder issues them)")
     ap.add_argument("--wc", action="store_true", help="write-combined pinned host input buffers (experiment)")
     ap.set_defaults(graph=True, overlap=True)
     args = ap.parse_args()

@@ -73,6 +73,7 @@ enum {
   SB_TUNE_TPS_LOG = 8,             /* TPS basis log(): 0 = lg2.approx * ln2 (default), 1 = libdevice logf */
   SB_TUNE_LOOKUP_PDL = 9,          /* r = 4 lookup launched with programmatic stream serialization (prologue overlaps the previous kernel's tail): 0 off, 1 on */
   SB_TUNE_CORR_A_TMEM = 10,        /* cost volume: 1 = the A block is copied to tensor memory once per unit and the MMAs read it from there */
+  SB_TUNE_LOOKUP_GENERIC = 11,     /* EXPERIMENT: 1 = r = 4 lookups take the generic window-staging kernel (LDG.128) instead of the TMA-box kernel */
   SB_TUNE_COUNT = 16
 };
 int sb_tune(int key, int value);
@@ -278,6 +279,21 @@ int sb_ccl(const float* feature_1, const float* feature_2, float* flow, void* wo
  * applied to the 3x3 zero-padded neighbourhood of 8 * flow [N, 2, H, W] -> out [N, 2, 8H, 8W]. */
 int sb_upsample_flow(const float* flow, const float* mask, float* out, int N, int H, int W,
                      sb_stream_t stream);
+
+/* ------------------------------------------------------------------ N4 ("next" row 4)
+ * Replaces the convolution stack of PatchEmbed.forward
+ * (core/FlowFormer/PerCostFormer3/encoder.py:36-43 built, :68-73 run; called per cost map at :263):
+ *   Conv2d(1,16,6,stride 2,pad 2) -> ReLU -> Conv2d(16,32,6,2,2) -> ReLU -> Conv2d(32,64,6,2,2)
+ * cost_maps [n_maps, 1, 64, 64] fp32 -> out [n_maps, 64, 8, 8] fp32.  bf16 operands, fp32 accumulation
+ * (tcgen05, CTA pairs); activations between the layers are rounded to bf16.
+ *   sb_patch_embed_pack: once per set of weights — w1 [16,1,6,6], w2 [32,16,6,6], w3 [64,32,6,6] fp32 ->
+ *     `pack` (sb_patch_embed_pack_bytes() bytes, 16-byte aligned), the kernel's shared-memory images.
+ *   bias: b1 | b2 | b3 = 16 + 32 + 64 fp32, contiguous.
+ * Only 64 x 64 maps (512 x 512 images, the shipped configuration) are supported: SB_EUNSUP otherwise. */
+size_t sb_patch_embed_pack_bytes(void);
+int sb_patch_embed_pack(const float* w1, const float* w2, const float* w3, void* pack, sb_stream_t stream);
+int sb_patch_embed_proj(const float* cost_maps, const void* pack, const float* bias, float* out,
+                        long long n_maps, int H, int W, sb_stream_t stream);
 
 /* ------------------------------------------------------------------ W4
  * Replaces compute_range_map(flow) (core/warp_utils.py:114-175): forward

@@ -245,6 +245,32 @@ def gma_aggregate(attn, fmap, to_v_weight, gamma, heads=1):
     return (fm + np.float32(gamma) * out).astype(np.float32)
 
 
+# ----------------------------------------------------------------- N4
+def _bf16(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).bfloat16().float().numpy()
+
+
+def conv6x6_s2(x, w, b):
+    """nn.Conv2d(kernel_size=6, stride=2, padding=2) in numpy (fp64 accumulation): x [N,C,H,W], w [O,C,6,6], b [O]."""
+    x = np.asarray(x, np.float64)
+    xp = np.pad(x, ((0, 0), (0, 0), (2, 2), (2, 2)))
+    win = np.lib.stride_tricks.sliding_window_view(xp, (6, 6), axis=(2, 3))[:, :, ::2, ::2]     # [N,C,OH,OW,6,6]
+    out = np.einsum("nchwyx,ocyx->nohw", win, np.asarray(w, np.float64), optimize=True)
+    return out + np.asarray(b, np.float64).reshape(1, -1, 1, 1)
+
+
+def patch_embed_proj(x, w1, b1, w2, b2, w3, b3, bf16_operands=False):
+    """The conv stack of PatchEmbed.forward (encoder.py:36-43,68-73): conv -> ReLU -> conv -> ReLU -> conv,
+    x [N,1,H,W] -> [N,64,H/8,W/8] fp32.  bf16_operands=True rounds the input, the weights and the two
+    intermediate activations to bf16 first — exactly what the tensor-core kernel contracts — so that the kernel
+    itself can be checked tightly, next to the looser contract against the fp32 reference."""
+    r = _bf16 if bf16_operands else (lambda a: np.asarray(a, np.float32))
+    a = np.maximum(conv6x6_s2(r(x), r(w1), b1), 0.0).astype(np.float32)
+    a = np.maximum(conv6x6_s2(r(a), r(w2), b2), 0.0).astype(np.float32)
+    return conv6x6_s2(r(a), r(w3), b3).astype(np.float32)
+
+
 # ----------------------------------------------------------------- N3
 def ccl(feature_1, feature_2, softmax_scale=10.0):
     """UDIS2Network.CCL (core/UDIS2/Homography/network.py:147-199) in numpy/fp64:

@@ -6,7 +6,7 @@ Importing the package needs only torch; the shared library (and a B200) is
 needed when a kernel is called. There is no CPU fallback.
 """
 from . import _lib  # noqa: F401
-from . import (adapter, composition, corr, decoder, gma, kornia_tps, lookup, patch, pipeline, torch_DLT,  # noqa: F401
+from . import (adapter, composition, corr, decoder, encoder, gma, kornia_tps, lookup, patch, pipeline, torch_DLT,  # noqa: F401
                torch_homo_transform, torch_tps_transform, udis2_homography, warp_utils)
 from .adapter import FlowHomoAdpater  # noqa: F401
 from .composition import build_model, composite_test_out, preprocess_occlusion_mask  # noqa: F401

@@ -57,6 +57,9 @@ SIGNATURES = {
     "sb_softmax_rows_bf16": (c_int, [_P, _P, c_longlong, c_int, c_longlong, _P]),
     "sb_attn_aggregate_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_upsample_flow": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "sb_patch_embed_pack_bytes": (c_size_t, []),
+    "sb_patch_embed_pack": (c_int, [_P, _P, _P, _P, _P]),
+    "sb_patch_embed_proj": (c_int, [_P, _P, _P, _P, c_longlong, c_int, c_int, _P]),
     "sb_range_map": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_morph_open": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_composite_test_out": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),

@@ -132,12 +132,16 @@ __device__ __forceinline__ float grid_roundtrip(float v, float den, float half) 
 // q = RN(a*r), q = fma(fma(-q, den, a), r, q), r = RN(1/den): bit-identical to div.rn for operands
 // in the normal range (Markstein; proven exhaustively over all mantissas by
 // tests/test_div_restatement.py), ~4 instructions instead of the ~15 of the generic division.
-__device__ __forceinline__ float grid_roundtrip_rcp(float v, float den, float rcp, float half) {
-  const float a = fmul(2.0f, v);
+// RN(a / den) for an INTEGER-valued den <= 2047 with rcp = RN(1 / den): the Markstein restatement above.
+__device__ __forceinline__ float div_small_int(float a, float den, float rcp) {
   float q = fmul(a, rcp);
   q = __fmaf_rn(__fmaf_rn(-q, den, a), rcp, q);
   const float aa = fabsf(a);
   if (!((aa > 1e-30f && aa < 1e30f) || aa == 0.0f)) q = fdiv(a, den);   // denormal range / huge / non-finite
+  return q;
+}
+__device__ __forceinline__ float grid_roundtrip_rcp(float v, float den, float rcp, float half) {
+  const float q = div_small_int(fmul(2.0f, v), den, rcp);
   return fmul(fadd(fsub(q, 1.0f), 1.0f), half);
 }
 

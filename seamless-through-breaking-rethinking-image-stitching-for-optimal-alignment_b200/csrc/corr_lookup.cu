@@ -537,7 +537,7 @@ extern "C" int sb_corr_lookup(const float* cost_maps, const float* coords, float
   long long blocks = (nq + kLookupWarps - 1) / kLookupWarps;
   const long long max_blocks = (long long)kNumSMs * 8 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
-  if (r == kFastR && (W2 & 3) == 0 && nq < (1ll << 30) && W2 <= 2048 && H2 <= 2048) {
+  if (r == kFastR && (W2 & 3) == 0 && nq < (1ll << 30) && W2 <= 2048 && H2 <= 2048 && !tune_get(SB_TUNE_LOOKUP_GENERIC, 0)) {
     const int hw1 = H1 * W1;
     const int vec_out = (out_stride == kFastTaps && out_offset == 0 && (hw1 % kFastQ) == 0 && aligned16(out)) ? 1 : 0;
     const int depth = tune_get(SB_TUNE_LOOKUP_DEPTH, 2);

@@ -101,7 +101,15 @@ constexpr int kSmemA = kMaxPanels * kPanelBytes;                 // 65536
 constexpr int kSmemB = kStages * kMaxPanels * kPanelBytes;       // 131072
 constexpr int kSmemStage = 4 * kSBufs * kStageBufBytes;          // 32768 with 2 buffers per warp
 constexpr int kSmemBar = 256;
-constexpr int kSmemTotal = kSmemA + kSmemB + kSmemStage + kSmemBar + 1024;  // + align slack
+// No alignment slack: the dynamic shared-memory array is declared __align__(1024) (SWIZZLE_128B tiles need it) and
+// the kernel traps if the base is not aligned.  224 KB + 256 B leaves room for the 1 KB-per-CTA reservations of two
+// more shared-memory-free CTAs on the SM (233 472 B per SM): the warp-stage kernels co-reside with this one.
+constexpr int kSmemTotal = kSmemA + kSmemB + kSmemStage + kSmemBar;
+// Register budget (SMX != 1): the kernel is registered at kRegsLaunch per thread (256 threads -> 38 912 of the SM's
+// 65 536 registers), warps 0-3 (TMA / MMA / TMEM / idle) shrink to kRegsLight and the four epilogue warps grow to
+// kRegsEpilogue with setmaxnreg; 4*32*(56 + 248) = 38 912.  The remaining 26 624 registers hold two 256-thread
+// CTAs of the instruction-bound gather kernels (32-40 registers per thread) next to this HBM-store-bound one.
+constexpr int kRegsLaunch = 152, kRegsLight = 56, kRegsEpilogue = 248;
 
 struct CorrParams {
   int B, N1, N2, KP;            // KP = Cpad / 64
@@ -155,12 +163,17 @@ __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, 2 ulp; -inf -> 
 // three accumulator buffers instead of four) and every MMA reads A from there: the shared-memory pipe, the
 // busiest unit of this kernel (ncu: 75-78 %), loses 48 of its ~320 KB per tile.
 template <int POOL, bool BF16OUT = false, bool TWO_CTA = false, int SMX = 0, bool ATMEM = false>
-__global__ void __launch_bounds__(SMX == 1 ? 384 : 256, 1)
+__global__ void __maxnreg__(SMX == 1 ? 168 : kRegsLaunch)
 corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_l1,
                  const __grid_constant__ CUtensorMap map_l2, const CorrParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if (smem_base & 1023u) {                       // never observed; a misaligned base would corrupt swizzled tiles
+    if (threadIdx.x == 0 && p.dbg) atomicExch(p.dbg, 0xDEAD00A1u);
+    __threadfence_system();
+    __trap();
+  }
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + kSmemA;
   const uint32_t sStage = sB + kSmemB;
@@ -221,6 +234,9 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t panel_tx = (uint32_t)p.KP * kPanelBytes;                 // A: this CTA's 128 rows
   const uint32_t b_tx = (uint32_t)p.KP * kBPanelBytes;                    // B: this CTA's share of a tile
 
+  if (warp < 4) {
+  // warpgroup 0 (one elected lane each for TMA and MMA issue): hand registers to the epilogue warpgroup
+  if (SMX != 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kRegsLight));
   if (warp == 0) {
     // ================================================================ producer
     if (lane == 0) {
@@ -314,7 +330,9 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  }
+  } else {
+    if (SMX != 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kRegsEpilogue));
     // ================================================================ epilogue
     const int wq = (warp - 4) & 3;                 // TMEM lane quarter == warp % 4
     const int quad = (warp - 4) >> 2;              // second epilogue quad: SMX == 1 only

@@ -57,22 +57,51 @@ homo_warp_kernel(const float* __restrict__ U, const float* __restrict__ theta,
     int32_t* d = idx_dbg + (size_t)b * 4 * oplane + rem;
     d[0] = tap.x0; d[oplane] = tap.x1; d[2 * (size_t)oplane] = tap.y0; d[3 * (size_t)oplane] = tap.y1;
   }
-  const float* src = U + (size_t)b * C * iplane;
-  float* dst = out + (size_t)b * Cout * oplane + rem;
+  // Channel loop: byte pointers stepped by the plane stride (one 64-bit add per pointer and channel).  A warp whose
+  // 32 pixels all have unclamped corners (x1 == x0 + 1, y1 == y0 + 1: everything but the image border) reads the east
+  // taps as +4-byte immediates of the two row pointers; the first version re-derived y*W + x and a 64-bit address for
+  // every tap of every channel (327 issued instructions per pixel for 12 loads and 6 stores, ncu round 1).
+  const size_t iplane_b = (size_t)iplane * sizeof(float), oplane_b = (size_t)oplane * sizeof(float);
+  const char* src = reinterpret_cast<const char*>(U) + (size_t)b * C * iplane_b;
+  char* dst = reinterpret_cast<char*>(out) + ((size_t)b * Cout * oplane + rem) * sizeof(float);
   if (n_ones > 0) {
     const float one = fadd(fadd(fadd(fmul(tap.wa, 1.0f), fmul(tap.wb, 1.0f)), fmul(tap.wc, 1.0f)),
                            fmul(tap.wd, 1.0f));
-    for (int ch = 0; ch < n_ones; ++ch) stg_stream(dst + (size_t)(C + ch) * oplane, one);
+    for (int ch = 0; ch < n_ones; ++ch) stg_stream(reinterpret_cast<float*>(dst + (size_t)(C + ch) * oplane_b), one);
   }
+  const bool interior = __all_sync(__activemask(), (tap.x1 == tap.x0 + 1) & (tap.y1 == tap.y0 + 1));
+  const char* p0 = src + ((size_t)tap.y0 * W + tap.x0) * sizeof(float);      // Ia; Ic = +4 when interior
+  const char* p1 = src + ((size_t)tap.y1 * W + tap.x0) * sizeof(float);      // Ib; Id = +4 when interior
+  const int east = (tap.x1 - tap.x0) * (int)sizeof(float);                   // 0 or 4 (per lane) on the border path
+  auto ld = [](const char* p, int byte_off) { return __ldg(reinterpret_cast<const float*>(p + byte_off)); };
+  auto mix = [&](float Ia, float Ib, float Ic, float Id) {
+    return fadd(fadd(fadd(fmul(tap.wa, Ia), fmul(tap.wb, Ib)), fmul(tap.wc, Ic)), fmul(tap.wd, Id));
+  };
   if (C_T > 0) {
     float v[C_T > 0 ? C_T : 1];
+    if (interior) {
 #pragma unroll
-    for (int ch = 0; ch < C_T; ++ch) v[ch] = tap.sample(src + (size_t)ch * iplane, W);
+      for (int ch = 0; ch < C_T; ++ch) {
+        v[ch] = mix(ld(p0, 0), ld(p1, 0), ld(p0, 4), ld(p1, 4));
+        p0 += iplane_b; p1 += iplane_b;
+      }
+    } else {
 #pragma unroll
-    for (int ch = 0; ch < C_T; ++ch) stg_stream(dst + (size_t)ch * oplane, v[ch]);
+      for (int ch = 0; ch < C_T; ++ch) {
+        v[ch] = mix(ld(p0, 0), ld(p1, 0), ld(p0, east), ld(p1, east));
+        p0 += iplane_b; p1 += iplane_b;
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < C_T; ++ch) {
+      stg_stream(reinterpret_cast<float*>(dst), v[ch]);
+      dst += oplane_b;
+    }
   } else {
-    for (int ch = 0; ch < C; ++ch)
-      stg_stream(dst + (size_t)ch * oplane, tap.sample(src + (size_t)ch * iplane, W));
+    for (int ch = 0; ch < C; ++ch) {
+      stg_stream(reinterpret_cast<float*>(dst), mix(ld(p0, 0), ld(p1, 0), ld(p0, east), ld(p1, east)));
+      p0 += iplane_b; p1 += iplane_b; dst += oplane_b;
+    }
   }
 }
 

@@ -56,11 +56,14 @@ def _lookup_into(cost_maps, coords, out, r, scale, stride, offset):
     _lib.check(rc, "sb_corr_lookup")
 
 
-def encode_flow_token(cost_maps, coords, r=4):
+def encode_flow_token(cost_maps, coords, r=4, out=None):
     """cost_maps ``[B*H1*W1, heads, H2, W2]``, coords ``[B,2,H1,W1]`` (x,y) ->
     ``[B, heads*(2r+1)^2, H1, W1]`` with the reference's memory order
     ``[B,H1,W1,heads*(2r+1)^2]``; channel ``k = i*(2r+1)+j`` samples
-    ``(cx + i - r, cy + j - r)`` (decoder.py:250-256, RAFT's meshgrid(dy,dx) quirk)."""
+    ``(cx + i - r, cy + j - r)`` (decoder.py:250-256, RAFT's meshgrid(dy,dx) quirk).
+
+    ``out`` (extension, heads == 1): a dense ``[B,H1,W1,(2r+1)^2]`` fp32 buffer to write into — e.g. a batch
+    slice of a larger result when the decoder loop runs per sub-batch of pairs."""
     cm = _lib.dev_f32(cost_maps, "cost_maps")
     co = _lib.dev_f32(coords, "coords")
     if cm.dim() != 4 or co.dim() != 4 or co.shape[1] != 2:
@@ -71,10 +74,16 @@ def encode_flow_token(cost_maps, coords, r=4):
         raise ValueError(f"encode_flow_token: {nq} cost maps for {b}x{h1}x{w1} queries")
     side = 2 * r + 1
     if heads == 1:
-        out = torch.empty((b, h1, w1, side * side), dtype=torch.float32, device=cm.device)
+        if out is None:
+            out = torch.empty((b, h1, w1, side * side), dtype=torch.float32, device=cm.device)
+        elif (tuple(out.shape) != (b, h1, w1, side * side) or out.dtype != torch.float32 or not out.is_contiguous()
+              or out.device != cm.device):
+            raise ValueError(f"encode_flow_token: out must be a dense fp32 [{b},{h1},{w1},{side * side}] tensor on {cm.device}")
         if nq:
             _lookup_into(cm, co, out, r, 1.0, side * side, 0)
         return out.permute(0, 3, 1, 2)
+    if out is not None:
+        raise ValueError("encode_flow_token: out= is only supported for heads == 1")
     # multi-head maps (not used by the shipped config, cost_heads_num=1): generic sampler
     d = torch.linspace(-r, r, side, device=cm.device)
     delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), dim=-1).view(1, side, side, 2)

@@ -14,7 +14,7 @@ __all__ = ["patch_reference"]
 
 
 def patch_reference(verbose: bool = False):
-    from . import composition, corr, decoder, gma, kornia_tps, lookup, udis2_homography, torch_homo_transform, torch_tps_transform, warp_utils
+    from . import composition, corr, decoder, encoder, gma, kornia_tps, lookup, udis2_homography, torch_homo_transform, torch_tps_transform, warp_utils
 
     done = []
 
@@ -41,6 +41,7 @@ def patch_reference(verbose: bool = False):
     _set("core.flowHomoAdpater", "warp", warp_utils.warp)                 # star-imported name (:16)
     _set("core.flowHomoAdpater", "compute_occlusion", warp_utils.compute_occlusion)
     _set("core.FlowFormer.PerCostFormer3.encoder", "corr", corr.memory_encoder_corr, cls="MemoryEncoder")
+    _set("core.FlowFormer.PerCostFormer3.encoder", "forward", encoder.patch_embed_forward, cls="PatchEmbed")
     _set("core.FlowFormer.PerCostFormer3.decoder", "encode_flow_token",
          lookup.memory_decoder_encode_flow_token, cls="MemoryDecoder")
     _set("core.FlowFormer.PerCostFormer3.decoder", "upsample_flow",

@@ -109,8 +109,14 @@ class HotPath:
     reference-shaped functions (the same calls a patched reference makes)."""
 
     def __init__(self, size: int = 512, iters: int = 12, pyramid: bool = True, r: int = 4, overlap: bool = True,
-                 eval_outputs: bool = False):
+                 eval_outputs: bool = False, lookup_subbatch: int = 0):
         self.size, self.iters, self.pyramid, self.r = size, iters, pyramid, r
+        # lookup_subbatch = n > 0: the decoder loop of a direction runs per sub-batch of n pairs (all `iters`
+        # lookups of pairs [0, n), then of [n, 2n), ...), so that the window lines a sub-batch touches (~14 MB per
+        # pair over 12 iterations) stay in the 126 MB L2 between iterations.  Same results, 1/n-th-size launches.
+        # Only meaningful where the decoder loop itself is run per sub-batch (its iteration t+1 centres come out
+        # of the GRU); 0 = one lookup per iteration over the whole batch, as the reference's decoder issues them.
+        self.lookup_subbatch = lookup_subbatch
         # eval_outputs: also produce the two tensors the reference's evaluation takes to the host
         # (evaluate.py:43-50) — used by the host-buffer pipeline, not part of the hot path itself
         self.eval_outputs = eval_outputs
@@ -118,7 +124,7 @@ class HotPath:
         # does not depend on the cost-volume stage (HBM-bound), so it runs on a second stream and
         # the GPU co-schedules the two; inside a captured graph this is a fork/join of two branches.
         self.overlap = overlap
-        self._side = None
+        self._side = self._main = None
         self._inflight = collections.deque()              # "step done" events of eager steps (see step())
         # bench.py sets this to a list to get (start, stop) CUDA events around every launch of
         # the dominant kernel (the tcgen05 cost volume) on the launching stream
@@ -203,10 +209,23 @@ class HotPath:
         maps_b = vol_b.view(b * s8 * s8, 1, s8, s8)
         # ---- 12 lookups per direction (MemoryDecoder.encode_flow_token)
         tokens = []
-        for it in range(iters):
-            tokens.append(lookup.encode_flow_token(maps_f, pb.coords[it], self.r))
-        for it in range(iters):
-            tokens.append(lookup.encode_flow_token(maps_b, pb.coords[iters + it], self.r))
+        nsb = self.lookup_subbatch
+        if nsb <= 0 or nsb >= b:
+            for it in range(iters):
+                tokens.append(lookup.encode_flow_token(maps_f, pb.coords[it], self.r))
+            for it in range(iters):
+                tokens.append(lookup.encode_flow_token(maps_b, pb.coords[iters + it], self.r))
+        else:
+            side2 = (2 * self.r + 1) ** 2
+            n1 = s8 * s8
+            bufs = [torch.empty((b, s8, s8, side2), dtype=torch.float32, device=maps_f.device) for _ in range(2 * iters)]
+            for d, maps in enumerate((maps_f, maps_b)):
+                for s0 in range(0, b, nsb):
+                    e0 = min(s0 + nsb, b)
+                    for it in range(iters):
+                        k = d * iters + it
+                        lookup.encode_flow_token(maps[s0 * n1:e0 * n1], pb.coords[k][s0:e0], self.r, out=bufs[k][s0:e0])
+            tokens = [t.permute(0, 3, 1, 2) for t in bufs]
         return dict(cost_tokens=tokens, cost_volume=vol_f, cost_volume_back=vol_b, cost_pyramid=pyr_f,
                     cost_pyramid_back=pyr_b)
 
@@ -225,11 +244,30 @@ class HotPath:
         else:
             if self._side is None:
                 self._side = torch.cuda.Stream(pb.image1.device)
-            side = self._side
+                # The cost-volume branch gets a HIGH-priority stream: its persistent CTAs (one per SM, 225 KB of
+                # shared memory) are placed as soon as an SM can take them instead of queueing behind the
+                # thousands of small warp-stage CTAs, which then fill the two CTA slots (registers + the 1 KB
+                # reservations) that the cost-volume kernel leaves free on every SM.
+                import os
+                prio = int(os.environ.get("STITCH_B200_COST_PRIORITY", "-1"))
+                self._main = torch.cuda.Stream(pb.image1.device, priority=prio) if prio != 0 else None
+            side, main = self._side, self._main
             side.wait_stream(cur)                             # fork
-            with torch.cuda.stream(side):
-                wout = self._warp_stage(pb)
-            out = self._cost_stage(pb)
+            if main is not None:
+                main.wait_stream(cur)
+                with torch.cuda.stream(main):
+                    out = self._cost_stage(pb)
+                with torch.cuda.stream(side):
+                    wout = self._warp_stage(pb)
+                cur.wait_stream(main)
+                for v in out.values():
+                    for t in (v if isinstance(v, (list, tuple)) else (v,)):
+                        if isinstance(t, torch.Tensor):
+                            t.record_stream(cur)
+            else:
+                with torch.cuda.stream(side):
+                    wout = self._warp_stage(pb)
+                out = self._cost_stage(pb)
             cur.wait_stream(side)                             # join
             for v in wout.values():
                 v.record_stream(cur)                          # produced on `side`, consumed on `cur`

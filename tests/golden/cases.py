@@ -175,6 +175,21 @@ def upsample_small():
     return dict(flow=torch.randn(2, 2, 12, 20, generator=g) * 3.0, mask=torch.randn(2, 576, 12, 20, generator=g) * 2.0)
 
 
+# ------------------------------------------------------------------ N4
+def patch_embed_small():
+    """Six 64x64 cost maps with the statistics of a real volume (dot products of 256 N(0,1) channels: std 16) and
+    nn.Conv2d-style seeded weights U(-1/sqrt(fan_in), 1/sqrt(fan_in))."""
+    g = _g(60)
+    x = torch.randn(6, 1, 64, 64, generator=g) * 16.0
+    x[5] = 0.0                                             # an all-zero map: output = the bias chain alone
+
+    def conv(o, c):
+        bound = 1.0 / (c * 36) ** 0.5
+        return ((torch.rand(o, c, 6, 6, generator=g) * 2 - 1) * bound, (torch.rand(o, generator=g) * 2 - 1) * bound)
+    (w1, b1), (w2, b2), (w3, b3) = conv(16, 1), conv(32, 16), conv(64, 32)
+    return dict(x=x, w1=w1, b1=b1, w2=w2, b2=b2, w3=w3, b3=b3)
+
+
 # ------------------------------------------------------------------ W3k
 def tps_kornia_small():
     """warp_image_tps inputs as tps_pipline.py:364-381 builds them: control points in pixels

@@ -209,6 +209,25 @@ def main():
     c = cases.ccl_small()
     save("ccl_small", cases.checksum(*c.values()), flow=UDIS2Network.CCL(stub, c["feature_1"], c["feature_2"]).numpy())
 
+    # ---------------------------------------------------------------- N4: the reference's own PatchEmbed (encoder.py:20-92)
+    # built as MemoryEncoder builds it (:179: patch_size 8, embed_dim = cost_latent_input_dim = 64, pe 'linear',
+    # patch_embed 'single'); the conv stack's output is captured with a forward hook on its last layer while
+    # the module's forward runs, the module's final tokens are stored too (for the drop-in forward body).
+    from core.FlowFormer.PerCostFormer3.encoder import PatchEmbed
+    c = cases.patch_embed_small()
+    torch.manual_seed(1234)
+    pe_mod = PatchEmbed(patch_size=8, in_chans=1, embed_dim=64, pe="linear",
+                        cfg=SimpleNamespace(patch_embed="single", use_rpe=False)).eval()
+    for idx, k in ((0, "1"), (2, "2"), (4, "3")):
+        pe_mod.proj[idx].weight.data.copy_(c["w" + k]); pe_mod.proj[idx].bias.data.copy_(c["b" + k])
+    grabbed = []
+    hook = pe_mod.proj[4].register_forward_hook(lambda m, i, o: grabbed.append(o.clone()))
+    tokens, size = pe_mod(c["x"])
+    hook.remove()
+    save("patch_embed_small", cases.checksum(*c.values()), proj=grabbed[0].numpy(), tokens=tokens.numpy(),
+         size=np.array(size), ffn0_w=pe_mod.ffn_with_coord[0].weight.detach().numpy(), ffn0_b=pe_mod.ffn_with_coord[0].bias.detach().numpy(),
+         ffn2_w=pe_mod.ffn_with_coord[2].weight.detach().numpy(), ffn2_b=pe_mod.ffn_with_coord[2].bias.detach().numpy())
+
     # ---------------------------------------------------------------- N2
     c = cases.upsample_small()
     save("upsample_small", cases.checksum(*c.values()), out=MemoryDecoder.upsample_flow(None, c["flow"], c["mask"]).numpy())

@@ -709,6 +709,113 @@ def test_next_rows_empty_and_bad_inputs(sb):
     assert tuple(sb.gma.attn_matmul_v(z(1, 66, 66), z(1, 128, 66)).shape) == (1, 128, 66)
 
 
+# ===================================================================== N4 (next row 4)
+def _pe_args(c):
+    return [cu(c[k]) for k in ("x", "w1", "b1", "w2", "b2", "w3", "b3")]
+
+
+def test_patch_embed_golden(sb):
+    """N4: the fused tcgen05 conv stack vs (1) the oracle on bf16-rounded operands (what the kernel contracts;
+    tight), (2) the reference's own PatchEmbed output (contract: 1e-2 of the output scale, bf16 operands vs fp32)."""
+    c = cases.patch_embed_small()
+    g = golden("patch_embed_small")
+    check_inputs(g, *c.values())
+    out = host(sb.encoder.patch_embed_proj(*_pe_args(c)))
+    assert out.shape == (6, 64, 8, 8)
+    scale = float(np.abs(g["proj"]).max())
+    a = {k: v.numpy() for k, v in c.items()}
+    assert max_abs(out, so.patch_embed_proj(**a, bf16_operands=True)) <= 2e-3 * scale      # fp32 vs fp64 accumulation, rare bf16 re-roundings
+    assert max_abs(out, g["proj"]) <= 1e-2 * scale
+    assert max_abs(out, so.patch_embed_proj(**a)) <= 1e-2 * scale
+    # module form with the reference's parameter names
+    m = sb.encoder.PatchEmbedProj().cuda()
+    m.load_state_dict({f"proj.{i}.{n}": c[f"{n[0]}{k}"] for i, k in ((0, 1), (2, 2), (4, 3)) for n in ("weight", "bias")}, strict=True)
+    assert torch.equal(m(cu(c["x"])), torch.from_numpy(out).cuda())
+
+
+def test_patch_embed_full_size_properties(sb):
+    """Two images' worth of cost maps plus a ragged tail (8195 maps: odd count, partial last wave): contract vs the
+    library convolutions on a sample, order independence (a map's result does not depend on which CTA / slot / wave
+    processed it), determinism, zero maps."""
+    c = cases.patch_embed_small()
+    g = torch.Generator(device="cuda").manual_seed(8)
+    n = 2 * 4096 + 3
+    x = torch.randn(n, 1, 64, 64, device="cuda", generator=g) * 16.0
+    x[17] = 0.0
+    args = _pe_args(c)[1:]
+    pack = sb.encoder.pack_patch_embed_weights(args[0], args[2], args[4])
+    out = sb.encoder.patch_embed_proj(x, *args, pack=pack)
+    torch.cuda.synchronize()
+    assert out.shape == (n, 64, 8, 8) and torch.isfinite(out).all()
+    sel = torch.tensor([0, 1, 2, 17, 147, 148, 149, 295, 296, 4095, 4096, 8191, 8192, 8193, 8194], device="cuda")
+    ref = x[sel]
+    for w, b, relu in ((args[0], args[1], True), (args[2], args[3], True), (args[4], args[5], False)):
+        ref = torch.nn.functional.conv2d(ref, w, b, stride=2, padding=2)
+        ref = torch.relu(ref) if relu else ref
+    scale = ref.abs().max().item()
+    assert (out[sel] - ref).abs().max().item() <= 1e-2 * scale
+    assert torch.equal(out, sb.encoder.patch_embed_proj(x, *args, pack=pack))               # deterministic
+    perm = torch.randperm(n, device="cuda", generator=g)
+    out_p = sb.encoder.patch_embed_proj(x[perm].contiguous(), *args, pack=pack)
+    assert torch.equal(out_p, out[perm])                                                     # order independent
+    one = sb.encoder.patch_embed_proj(x[4097:4098].contiguous(), *args, pack=pack)           # a single map (half-empty pair)
+    assert torch.equal(one[0], out[4097])
+    z = sb.encoder.patch_embed_proj(torch.zeros(1, 1, 64, 64, device="cuda"), *args, pack=pack)
+    assert torch.equal(z[0], out[17])
+    with pytest.raises(NotImplementedError, match="64x64"):
+        sb.encoder.patch_embed_proj(torch.zeros(2, 1, 32, 32, device="cuda"), *args)
+    assert sb.encoder.patch_embed_proj(torch.zeros(0, 1, 64, 64, device="cuda"), *args).shape == (0, 64, 8, 8)
+
+
+def coords_grid(batch, ht, wd):                      # core/utils/utils.py:97-100 (used by the drop-in forward below)
+    ys, xs = torch.meshgrid(torch.arange(ht), torch.arange(wd), indexing="ij")
+    return torch.stack([xs, ys], dim=0).float()[None].repeat(batch, 1, 1, 1)
+
+
+def LinearPositionEmbeddingSine(x, dim=128, NORMALIZE_FACOR=1 / 200):      # attention.py:156-161 of the reference
+    fb = torch.linspace(0, dim // 4 - 1, dim // 4).to(x.device)
+    return torch.cat([torch.sin(3.14 * x[..., -2:-1] * fb * NORMALIZE_FACOR), torch.cos(3.14 * x[..., -2:-1] * fb * NORMALIZE_FACOR),
+                      torch.sin(3.14 * x[..., -1:] * fb * NORMALIZE_FACOR), torch.cos(3.14 * x[..., -1:] * fb * NORMALIZE_FACOR)], dim=-1)
+
+
+class _PatchEmbedShell(torch.nn.Module):
+    """A module with the reference PatchEmbed's attributes (encoder.py:20-58); its forward IS the drop-in body.
+    The body takes coords_grid / LinearPositionEmbeddingSine from the defining module of type(self), as it does
+    for the reference class — here: this test module (restated above, network code outside the hot path)."""
+
+    def __init__(self):
+        super().__init__()
+        from types import SimpleNamespace
+        import stitch_b200
+        self.patch_size, self.dim, self.pe, self.cfg = 8, 64, "linear", SimpleNamespace(patch_embed="single", use_rpe=False)
+        self.proj = stitch_b200.encoder.PatchEmbedProj().proj
+        self.ffn_with_coord = torch.nn.Sequential(torch.nn.Conv2d(128, 128, 1), torch.nn.ReLU(), torch.nn.Conv2d(128, 128, 1))
+        self.norm = torch.nn.LayerNorm(128)
+
+    def forward(self, x, *masks):
+        import stitch_b200
+        return stitch_b200.encoder.patch_embed_forward(self, x, *masks)
+
+
+def test_patch_embed_forward_dropin(sb):
+    """PatchEmbed.forward with the conv stack replaced by the kernel vs the reference module's own tokens."""
+    c = cases.patch_embed_small()
+    g = golden("patch_embed_small")
+    m = _PatchEmbedShell()
+    for i, k in ((0, 1), (2, 2), (4, 3)):
+        m.proj[i].weight.data.copy_(c[f"w{k}"]); m.proj[i].bias.data.copy_(c[f"b{k}"])
+    for i in (0, 2):
+        m.ffn_with_coord[i].weight.data.copy_(torch.from_numpy(g[f"ffn{i}_w"])); m.ffn_with_coord[i].bias.data.copy_(torch.from_numpy(g[f"ffn{i}_b"]))
+    m = m.cuda().eval()
+    tokens, size = m(cu(c["x"]))
+    assert tuple(size) == tuple(g["size"]) == (8, 8) and tokens.shape == g["tokens"].shape == (6, 64, 128)
+    assert max_abs(host(tokens), g["tokens"]) <= 3e-2          # LayerNorm output, O(1): bf16 conv stack vs fp32
+    # a pre-training mask disables the fused path: the module's own layers run, as in the reference
+    mask1 = torch.zeros(6, 1, 64, 64, device="cuda")
+    t2, _ = m(cu(c["x"]), mask1, None, None)
+    assert max_abs(host(t2), g["tokens"]) <= 1e-2              # cuDNN convolutions (TF32 allowed by default) vs the CPU run
+
+
 # ===================================================================== N2 (next row 2)
 def test_upsample_flow_golden(sb):
     c = cases.upsample_small()

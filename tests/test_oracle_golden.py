@@ -259,6 +259,24 @@ def test_tps_mix():
     assert_bits_equal(blend, g["blend"], "blend")
 
 
+# ---------------------------------------------------------------- N4
+def test_patch_embed_proj():
+    """The oracle's conv stack against the reference's own PatchEmbed (output of its last conv, captured while the
+    module's forward ran): fp32 summation-order noise only.  The bf16-operand emulation of the tensor-core kernel
+    stays within the 1e-2-of-scale contract of the fp32 reference."""
+    c = cases.patch_embed_small()
+    g = golden("patch_embed_small")
+    check_inputs(g, *c.values())
+    a = {k: v.numpy() for k, v in c.items()}
+    scale = float(np.abs(g["proj"]).max())
+    out = so.patch_embed_proj(**a)
+    assert out.shape == g["proj"].shape == (6, 64, 8, 8)
+    assert max_abs(out, g["proj"]) <= 2e-5 * scale
+    assert max_abs(so.patch_embed_proj(**a, bf16_operands=True), g["proj"]) <= 1e-2 * scale
+    # the all-zero map: every layer sees only its bias through the zero padding pattern
+    assert max_abs(out[5, :, 3, 3], so.patch_embed_proj(np.zeros((1, 1, 64, 64), np.float32), *[a[k] for k in ("w1", "b1", "w2", "b2", "w3", "b3")])[0, :, 3, 3]) == 0.0
+
+
 # ---------------------------------------------------------------- G1
 def test_dlt():
     g = golden("geometry")

@@ -116,6 +116,24 @@ def main():
     ms = timeit(lambda: sb.udis2_homography.CCL(cf1, cf2), n=10)
     report("CCL (norm + tf32 corr + softmax-flow)", ms, B * (2 * 1024 * 1024 * 4 * 3 + 1024 * 1024 * 4 * 2))
     print(f"{'':34s} {B*2*1024*1024*1024/ms/1e9:.0f} TFLOP/s on the contraction actually computed; reference form = 9x the FLOPs")
+    # ---- PatchEmbed projection (next row 4): one direction's 65536 cost maps
+    if os.environ.get("SB_BENCH_PATCH_EMBED", "1") == "1":
+        vol4 = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64)).view(B * n, 1, 64, 64)
+        gw = lambda o, c: ((torch.rand(o, c, 6, 6, device="cuda", generator=g) * 2 - 1) / (c * 36) ** 0.5, (torch.rand(o, device="cuda", generator=g) * 2 - 1) / (c * 36) ** 0.5)
+        (pw1, pb1), (pw2, pb2), (pw3, pb3) = gw(16, 1), gw(32, 16), gw(64, 32)
+        pack = sb.encoder.pack_patch_embed_weights(pw1, pw2, pw3)
+        ms = timeit(lambda: sb.encoder.patch_embed_proj(vol4, pw1, pb1, pw2, pb2, pw3, pb3, pack=pack), n=5, warm=2)
+        report("patch_embed proj (3 convs, tcgen05)", ms, B * n * 2 * 16384)
+        fl = B * n * 2.0 * (1024 * 16 * 36 + 256 * 32 * 576 + 64 * 64 * 1152)
+        print(f"{'':34s} tensor: {fl/ms/1e9:.0f} TFLOP/s useful = {100*fl/ms/1e9/TP.get('bf16_tflops_sustained', 1404.5):.0f}% of sustained bf16 peak")
+        x8 = vol4[:8192]
+        def _torch_ref():
+            a = torch.relu(torch.nn.functional.conv2d(x8, pw1, pb1, stride=2, padding=2))
+            a = torch.relu(torch.nn.functional.conv2d(a, pw2, pb2, stride=2, padding=2))
+            return torch.nn.functional.conv2d(a, pw3, pb3, stride=2, padding=2)
+        ms8 = timeit(_torch_ref, n=3, warm=1)
+        print(f"{'':34s} torch/cuDNN fp32 convs (the reference's path) on 8192 maps: {ms8*1e3:.0f} us -> {ms8*8*1e3:.0f} us per 65536 maps")
+        del vol4, x8
     lo2, um = rnd(B, 2, 64, 64), rnd(B, 576, 64, 64)
     report("upsample_flow (convex 8x)", timeit(lambda: sb.decoder.upsample_flow(lo2, um)), B * 4096 * (576 + 128 + 2) * 4)
     ys, xs = torch.meshgrid(torch.linspace(-1, 1, 13, device="cuda"), torch.linspace(-1, 1, 13, device="cuda"), indexing="ij")

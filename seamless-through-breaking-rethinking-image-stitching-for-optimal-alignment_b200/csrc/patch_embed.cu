@@ -26,10 +26,11 @@
 //
 // Machine mapping.  The bf16 weights (186 KB) do not fit one SM next to the activations, so the kernel runs as
 // clusters of two CTAs with tcgen05.mma.cta_group::2: M = 256 per instruction — each CTA supplies the 128 rows of
-// ITS OWN cost map and HALF of the weight rows (N/2), 93 KB per SM.  Per CTA: warps 0 / 2 / 3 = MMA issuers of
-// conv1 / conv2 / conv3 (leader CTA, one lane each), warp 1 = TMEM allocator, warps 4-7 = epilogues (TMEM lane
-// quarters), warps 8-11 = loaders (fp32 map -> bf16 space-to-depth entries).  The three layers run on three
-// consecutive maps at once (conv1(t), conv2(t-1), conv3(t-2)): every epilogue runs under the other layers' MMAs.
+// ITS OWN cost map and HALF of the weight rows (N/2), 93 KB per SM.  Per CTA (16 warps): warps 0 / 2 / 3 = MMA
+// issuers of conv1 / conv2 / conv3 (leader CTA), warp 1 = TMEM allocator, warps 4-7 and 8-11 = two epilogue sets
+// (TMEM lane quarter = warp % 4), warps 12-15 = loaders (fp32 map -> bf16 space-to-depth entries).  The three
+// layers run on three consecutive maps at once (conv1(t), conv2(t-1), conv3(t-2)); the conv2 / conv3 accumulators
+// are double-buffered in tensor memory, so an epilogue only ever serialises with the MMAs that read what it writes.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -38,7 +39,7 @@
 namespace sb {
 namespace pe {
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;
 // ---- flat activation geometry (entries of 16 bytes)
 constexpr int kRow1 = 33, kRow2 = 17, kRow3 = 9;          // OW + 1 of conv1 / conv2 / conv3
 constexpr int kMB1 = 9, kMB2 = 3, kMB3 = 1;               // 128-row M blocks per map
@@ -66,7 +67,8 @@ constexpr int kSmemTotal = oBar + 256;
 static_assert(oA1 % 16 == 0 && oA2 % 16 == 0 && oA3 % 16 == 0 && oStage % 16 == 0 && oBar % 8 == 0, "alignment");
 static_assert(kSmemTotal <= 232448, "shared memory budget");
 // ---- tensor memory columns
-constexpr int kD1Col = 0, kD2Col = kMB1 * 16, kD3Col = kD2Col + kMB2 * 32;   // 0, 144, 240 (+64 = 304 <= 512)
+constexpr int kD2Cols = kMB2 * 32, kD3Cols = 64;                            // one accumulator set of conv2 / conv3
+constexpr int kD1Col = 0, kD2Col = kMB1 * 16, kD3Col = kD2Col + 2 * kD2Cols;  // D1 144 | D2 x2 192 | D3 x2 128 = 464 <= 512
 constexpr int kTmemCols = 512;
 
 // instruction descriptor: D = f32, A = B = bf16, both K-major, M = 256 (CTA pair), N = n
@@ -140,28 +142,30 @@ patch_embed_umma_kernel(const Params p) {
   const bool leader = rank == 0;
   const long long cluster_id = blockIdx.x >> 1;
 
-  // barriers (8 bytes each, same offsets in both CTAs)
+  // barriers (8 bytes each, same offsets in both CTAs).  "leader": only the leader CTA's copy is used, both CTAs'
+  // warps arrive on it through shared::cluster; "both": a multicast tcgen05.commit arrives on each CTA's copy.
+  // Everything that is double-buffered has one barrier per buffer, so that a waiter is never more than one phase behind.
   const uint32_t bar = sm + oBar;
   const uint32_t bar_w = bar + 0;                  // weights landed (local, tx)
-  const uint32_t bar_ldr_full = bar + 8;           // [2] leader: 8 loader-warp arrivals (both CTAs)
-  const uint32_t bar_a1_free = bar + 24;           // [2] both: conv1 MMAs of that buffer retired
+  const uint32_t bar_ldr_full = bar + 8;           // [2] leader: 8 loader-warp arrivals
+  const uint32_t bar_a1_free = bar + 24;           // [2] both: conv1 MMAs of that A1 buffer retired
   const uint32_t bar_d1_full = bar + 40;           // both: conv1 accumulators ready
-  const uint32_t bar_m2_done = bar + 48;           // both: conv2 MMAs retired (D2 ready, A2 reusable)
-  const uint32_t bar_m3_done = bar + 56;           // both: conv3 MMAs retired (D3 ready, A3 reusable)
-  const uint32_t bar_e1_done = bar + 64;           // leader: 8 epilogue-warp arrivals (D1 drained, A2 written)
-  const uint32_t bar_e2_done = bar + 72;           // leader: D2 drained, A3 written
-  const uint32_t bar_e3_done = bar + 80;           // leader: D3 drained
-  const uint32_t tmem_slot = bar + 96;
+  const uint32_t bar_m2_done = bar + 48;           // [2] both: conv2 into D2[i] retired (D2[i] ready, A2 reusable)
+  const uint32_t bar_m3_done = bar + 64;           // [2] both: conv3 into D3[i] retired (D3[i] ready, A3 reusable)
+  const uint32_t bar_e1_done = bar + 80;           // leader: 16 epilogue-warp arrivals (D1 drained, A2 written)
+  const uint32_t bar_e2_done = bar + 88;           // [2] leader: 8 arrivals (D2[i] drained, A3 written)
+  const uint32_t bar_e3_done = bar + 104;          // [2] leader: 8 arrivals (D3[i] drained)
+  const uint32_t tmem_slot = bar + 128;
 
   if (threadIdx.x == 0) {
     ptx::mbar_init(bar_w, 1);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bar_ldr_full + 8 * i, 8); ptx::mbar_init(bar_a1_free + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_ldr_full + 8 * i, 8); ptx::mbar_init(bar_a1_free + 8 * i, 1);
+      ptx::mbar_init(bar_m2_done + 8 * i, 1);  ptx::mbar_init(bar_m3_done + 8 * i, 1);
+      ptx::mbar_init(bar_e2_done + 8 * i, 8);  ptx::mbar_init(bar_e3_done + 8 * i, 8);
+    }
     ptx::mbar_init(bar_d1_full, 1);
-    ptx::mbar_init(bar_m2_done, 1);
-    ptx::mbar_init(bar_m3_done, 1);
-    ptx::mbar_init(bar_e1_done, 8);
-    ptx::mbar_init(bar_e2_done, 8);
-    ptx::mbar_init(bar_e3_done, 8);
+    ptx::mbar_init(bar_e1_done, 16);
     ptx::fence_mbar_init();
     // this CTA's half of the weights: three bulk copies, one transaction barrier
     ptx::mbar_arrive_expect_tx(bar_w, kWBytes);
@@ -182,21 +186,22 @@ patch_embed_umma_kernel(const Params p) {
   ptx::mbar_wait(bar_w, 0, 1, p.dbg);               // every thread: the weight bytes are visible
   ptx::cluster_sync_all();                          // peer's barriers, weights and zeroed buffers are ready
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + oBar + 96);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + oBar + 128);
   const int T = p.iters;
+  const float* bias = reinterpret_cast<const float*>(smem_raw + oBias);
 
   if (warp == 0 || warp == 2 || warp == 3) {
-    // ================================================================ MMA issuers (leader CTA, one lane each)
-    // One issuing thread per layer: N = 16 / 32 / 64 instructions execute in 8 / 16 / 32 cycles, less than it takes
+    // ================================================================ MMA issuers (leader CTA, one warp each)
+    // One issuing warp per layer: N = 16 / 32 / 64 instructions execute in 8 / 16 / 32 cycles, less than it takes
     // one thread to issue them back to back (first version: 207 MMAs per iteration from one thread, 87 cycles each
     // with the descriptors rebuilt per instruction -> 4.2 ms per 65 536 maps).  Descriptors are a constant high word
-    // and a running low word (14-bit address field + LBO): one uniform add per operand and instruction.
-    if (leader && lane == 0) {
+    // and a running low word (14-bit address field + LBO): one add per operand and instruction.
+    if (leader) {                    // the whole warp runs the loop (converged); one elected lane issues each instruction
       const uint32_t kHi = (128u >> 4) | (1u << 14);                   // SBO = 128 B, descriptor version 1
       auto lo_of = [](uint32_t addr, uint32_t lbo_bytes) { return ((addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); };
       auto d64 = [&](uint32_t lo) { return ((uint64_t)kHi << 32) | (uint64_t)lo; };
       if (warp == 0) {
-        // ---------------- conv1: map t when its entries are loaded and D1 is drained
+        // ---------------- conv1(t): needs the entries of map t (loaders) and D1 drained (E1(t-1))
         const uint32_t b_lo = lo_of(sm + oW1, 128u);
         for (int t = 0; t < T; ++t) {
           const int buf = t & 1;
@@ -209,71 +214,75 @@ patch_embed_umma_kernel(const Params p) {
           for (int mb = 0; mb < kMB1; ++mb) {
 #pragma unroll
             for (int ks = 0; ks < 3; ++ks)        // ks = dy + 1: input row oy + dy
-              ptx::umma_f16_2cta(d, d64(a_lo + (uint32_t)(kRow1 * ks)), d64(b_lo + (uint32_t)(ks * 16)), idesc(16), ks != 0);
+              ptx::umma_f16_2cta_elect(d, d64(a_lo + (uint32_t)(kRow1 * ks)), d64(b_lo + (uint32_t)(ks * 16)), idesc(16), ks != 0);
             a_lo += 128u; d += 16u;
           }
-          ptx::umma_commit_2cta(bar_a1_free + 8 * buf, 3);
-          ptx::umma_commit_2cta(bar_d1_full, 3);
+          ptx::umma_commit_2cta_elect(bar_a1_free + 8 * buf, 3);
+          ptx::umma_commit_2cta_elect(bar_d1_full, 3);
         }
       } else if (warp == 2) {
-        // ---------------- conv2: map t when E1(t) has written A2 and E2(t-1) has drained D2
+        // ---------------- conv2(t) -> D2[t & 1]: needs A2 written (E1(t)) and that accumulator drained (E2(t-2))
         const uint32_t a_base = lo_of(sm + oA2, kCh2 * 16u), b_base = lo_of(sm + oW2, 256u);
         for (int t = 0; t < T; ++t) {
+          const int buf = t & 1;
           ptx::mbar_wait(bar_e1_done, (uint32_t)(t & 1), 4, p.dbg);
-          if (t >= 1) ptx::mbar_wait(bar_e2_done, (uint32_t)((t - 1) & 1), 5, p.dbg);
+          if (t >= 2) ptx::mbar_wait(bar_e2_done + 8 * buf, (uint32_t)(((t >> 1) - 1) & 1), 5, p.dbg);
           ptx::tc_fence_after_sync();
-          uint32_t a_lo = a_base, d = tmem_base + kD2Col;
+          uint32_t a_lo = a_base, d = tmem_base + kD2Col + buf * kD2Cols;
 #pragma unroll 1
           for (int mb = 0; mb < kMB2; ++mb) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                ptx::umma_f16_2cta(d, d64(a_lo + (uint32_t)(kRow2 * (tap / 3) + (tap % 3) + 2 * j * kCh2)),
-                                   d64(b_base + (uint32_t)((tap * 8 + 2 * j) * 16)), idesc(32), (tap | j) != 0);
+                ptx::umma_f16_2cta_elect(d, d64(a_lo + (uint32_t)(kRow2 * (tap / 3) + (tap % 3) + 2 * j * kCh2)),
+                                         d64(b_base + (uint32_t)((tap * 8 + 2 * j) * 16)), idesc(32), (tap | j) != 0);
             }
             a_lo += 128u; d += 32u;
           }
-          ptx::umma_commit_2cta(bar_m2_done, 3);
+          ptx::umma_commit_2cta_elect(bar_m2_done + 8 * buf, 3);
         }
       } else {
-        // ---------------- conv3: map t when E2(t) has written A3 and E3(t-1) has drained D3
+        // ---------------- conv3(t) -> D3[t & 1]: needs A3 written (E2(t)) and that accumulator drained (E3(t-2))
         const uint32_t a_base = lo_of(sm + oA3, kCh3 * 16u), b_base = lo_of(sm + oW3, 512u);
-        const uint32_t d = tmem_base + kD3Col;
         for (int t = 0; t < T; ++t) {
-          ptx::mbar_wait(bar_e2_done, (uint32_t)(t & 1), 6, p.dbg);
-          if (t >= 1) ptx::mbar_wait(bar_e3_done, (uint32_t)((t - 1) & 1), 13, p.dbg);
+          const int buf = t & 1;
+          ptx::mbar_wait(bar_e2_done + 8 * buf, (uint32_t)((t >> 1) & 1), 6, p.dbg);
+          if (t >= 2) ptx::mbar_wait(bar_e3_done + 8 * buf, (uint32_t)(((t >> 1) - 1) & 1), 13, p.dbg);
           ptx::tc_fence_after_sync();
+          const uint32_t d = tmem_base + kD3Col + buf * kD3Cols;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              ptx::umma_f16_2cta(d, d64(a_base + (uint32_t)(kRow3 * (tap / 3) + (tap % 3) + 2 * j * kCh3)),
-                                 d64(b_base + (uint32_t)((tap * 16 + 2 * j) * 32)), idesc(64), (tap | j) != 0);
+              ptx::umma_f16_2cta_elect(d, d64(a_base + (uint32_t)(kRow3 * (tap / 3) + (tap % 3) + 2 * j * kCh3)),
+                                       d64(b_base + (uint32_t)((tap * 16 + 2 * j) * 32)), idesc(64), (tap | j) != 0);
           }
-          ptx::umma_commit_2cta(bar_m3_done, 3);
+          ptx::umma_commit_2cta_elect(bar_m3_done + 8 * buf, 3);
         }
       }
     }
     __syncwarp();
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ================================================================ loaders: fp32 map -> bf16 s2d pair entries
-    const int tid = threadIdx.x - 256;               // 0..127
+    const int tid = threadIdx.x - 384;               // 0..127
     const uint32_t full_tgt0 = ptx::mapa_shared(bar_ldr_full, 0);
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const long long q = ((long long)t * p.nclusters + cluster_id) * 2 + rank;
-      if (t >= 2) ptx::mbar_wait(bar_a1_free + 8 * buf, (uint32_t)(((t >> 1) - 1) & 1), 7, p.dbg);
-      if (q < p.nq) {
+      float2 top[8], bot[8];
+      if (q < p.nq) {                                // issue the global loads before waiting for the buffer
         const float* src = p.maps + q * 4096;
-        const uint32_t a1 = sm + oA1 + buf * kA1Bytes;
-        float2 top[8], bot[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {                // s2d position (r, i) = (pos >> 5, pos & 31), pos = tid + 128 j
           const int pos = tid + 128 * j, r = pos >> 5, i = pos & 31;
           top[j] = ldg_stream2(src + (2 * r) * 64 + 2 * i);
           bot[j] = ldg_stream2(src + (2 * r + 1) * 64 + 2 * i);
         }
+      }
+      if (t >= 2) ptx::mbar_wait(bar_a1_free + 8 * buf, (uint32_t)(((t >> 1) - 1) & 1), 7, p.dbg);
+      if (q < p.nq) {
+        const uint32_t a1 = sm + oA1 + buf * kA1Bytes;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int pos = tid + 128 * j, r = pos >> 5, i = pos & 31;
@@ -288,32 +297,41 @@ patch_embed_umma_kernel(const Params p) {
       if (lane == 0) ptx::mbar_arrive_cluster(full_tgt0 + 8 * buf);
     }
   } else if (warp >= 4) {
-    // ================================================================ epilogues
-    const int wq = warp - 4;                          // TMEM lane quarter
+    // ================================================================ epilogues: two warp sets (TMEM lane quarter = warp % 4)
+    //   set A (warps 4-7):  E1 blocks 0..4 of map t, then E3 of map t-2 (+ the output store)
+    //   set B (warps 8-11): E1 blocks 5..8 of map t, then E2 of map t-1
+    const int wq = warp & 3;
+    const bool set_a = warp < 8;
     const uint32_t lane_t = tmem_base + ((uint32_t)(wq * 32) << 16);
-    const float* bias = reinterpret_cast<const float*>(smem_raw + oBias);
     const uint32_t e1_tgt = ptx::mapa_shared(bar_e1_done, 0), e2_tgt = ptx::mapa_shared(bar_e2_done, 0),
                    e3_tgt = ptx::mapa_shared(bar_e3_done, 0);
-    const int etid = threadIdx.x - 128;               // 0..127
+    const int etid = threadIdx.x - 128;               // set A: 0..127
     for (int t = 0; t < T + 2; ++t) {
       // ---------------- E1(t): D1 -> bias, ReLU, bf16 -> conv2's flat s2d buffer
       if (t < T) {
         ptx::mbar_wait(bar_d1_full, (uint32_t)(t & 1), 8, p.dbg);
-        if (t >= 1) ptx::mbar_wait(bar_m2_done, (uint32_t)((t - 1) & 1), 9, p.dbg);     // conv2(t-1) has read A2
+        if (t >= 1) ptx::mbar_wait(bar_m2_done + 8 * ((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), 9, p.dbg);   // conv2(t-1) has read A2
         ptx::tc_fence_after_sync();
+        const int mb0 = set_a ? 0 : 5, mb1 = set_a ? 5 : kMB1;
+        uint32_t r[2][16];
+        tmem_ld_x16(lane_t + kD1Col + mb0 * 16, r[0]);
 #pragma unroll 1
-        for (int mb = 0; mb < kMB1; ++mb) {
-          uint32_t r[16];
-          tmem_ld_x16(lane_t + kD1Col + mb * 16, r);
+        for (int mb = mb0; mb < mb1; ++mb) {
+          const int cur = (mb - mb0) & 1;
           ptx::tmem_ld_wait();
+          if (mb + 1 < mb1) {                          // next block's load in flight while this one is converted
+            if (cur == 0) tmem_ld_x16(lane_t + kD1Col + (mb + 1) * 16, r[1]);
+            else tmem_ld_x16(lane_t + kD1Col + (mb + 1) * 16, r[0]);
+          }
           const int m = mb * 128 + wq * 32 + lane;
           const int oy = m / kRow1, ox = m - oy * kRow1;
           if (oy < 32 && ox < 32) {
             uint32_t w[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              w[c] = pack_bf16(fmaxf(__uint_as_float(r[2 * c]) + bias[2 * c], 0.0f),
-                               fmaxf(__uint_as_float(r[2 * c + 1]) + bias[2 * c + 1], 0.0f));
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t x0 = cur == 0 ? r[0][2 * c] : r[1][2 * c], x1 = cur == 0 ? r[0][2 * c + 1] : r[1][2 * c + 1];
+              w[c] = pack_bf16(fmaxf(__uint_as_float(x0) + bias[2 * c], 0.0f), fmaxf(__uint_as_float(x1) + bias[2 * c + 1], 0.0f));
+            }
             // s2d channel (py, px, c1) -> chunk (py*2 + px)*2 + c1/8 at entry 1 + (oy/2 + 1) * 17 + ox/2
             const uint32_t chunk = (uint32_t)(((oy & 1) * 2 + (ox & 1)) * 2);
             const uint32_t e = sm + oA2 + (chunk * kCh2 + (uint32_t)(1 + ((oy >> 1) + 1) * kRow2 + (ox >> 1))) * 16u;
@@ -326,71 +344,76 @@ patch_embed_umma_kernel(const Params p) {
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(e1_tgt);
       }
-      // ---------------- E2(t-1): D2 -> conv3's flat s2d buffer
-      if (t >= 1 && t <= T) {
-        ptx::mbar_wait(bar_m2_done, (uint32_t)((t - 1) & 1), 10, p.dbg);
-        if (t >= 2) ptx::mbar_wait(bar_m3_done, (uint32_t)((t - 2) & 1), 11, p.dbg);    // conv3(t-2) has read A3
-        ptx::tc_fence_after_sync();
+      if (!set_a) {
+        // ---------------- E2(t-1): D2[(t-1) & 1] -> conv3's flat s2d buffer
+        if (t >= 1 && t <= T) {
+          const int u = t - 1, buf = u & 1;
+          ptx::mbar_wait(bar_m2_done + 8 * buf, (uint32_t)((u >> 1) & 1), 10, p.dbg);
+          if (u >= 1) ptx::mbar_wait(bar_m3_done + 8 * ((u - 1) & 1), (uint32_t)(((u - 1) >> 1) & 1), 11, p.dbg);   // conv3(u-1) has read A3
+          ptx::tc_fence_after_sync();
 #pragma unroll 1
-        for (int mb = 0; mb < kMB2; ++mb) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(lane_t + kD2Col + mb * 32, r);
-          ptx::tmem_ld_wait();
-          const int m = mb * 128 + wq * 32 + lane;
-          const int oy = m / kRow2, ox = m - oy * kRow2;
-          if (oy < 16 && ox < 16) {
-            const uint32_t chunk = (uint32_t)(((oy & 1) * 2 + (ox & 1)) * 4);
-            const uint32_t e = sm + oA3 + (chunk * kCh3 + (uint32_t)(1 + ((oy >> 1) + 1) * kRow3 + (ox >> 1))) * 16u;
+          for (int mb = 0; mb < kMB2; ++mb) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(lane_t + kD2Col + buf * kD2Cols + mb * 32, r);
+            ptx::tmem_ld_wait();
+            const int m = mb * 128 + wq * 32 + lane;
+            const int oy = m / kRow2, ox = m - oy * kRow2;
+            if (oy < 16 && ox < 16) {
+              const uint32_t chunk = (uint32_t)(((oy & 1) * 2 + (ox & 1)) * 4);
+              const uint32_t e = sm + oA3 + (chunk * kCh3 + (uint32_t)(1 + ((oy >> 1) + 1) * kRow3 + (ox >> 1))) * 16u;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t w[4];
+              for (int g = 0; g < 4; ++g) {
+                uint32_t w[4];
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                w[c] = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 2 * c]) + bias[16 + 8 * g + 2 * c], 0.0f),
-                                 fmaxf(__uint_as_float(r[8 * g + 2 * c + 1]) + bias[16 + 8 * g + 2 * c + 1], 0.0f));
-              sts128(e + (uint32_t)g * (kCh3 * 16u), w[0], w[1], w[2], w[3]);
+                for (int c = 0; c < 4; ++c)
+                  w[c] = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 2 * c]) + bias[16 + 8 * g + 2 * c], 0.0f),
+                                   fmaxf(__uint_as_float(r[8 * g + 2 * c + 1]) + bias[16 + 8 * g + 2 * c + 1], 0.0f));
+                sts128(e + (uint32_t)g * (kCh3 * 16u), w[0], w[1], w[2], w[3]);
+              }
             }
           }
+          ptx::fence_proxy_async_smem();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(e2_tgt + 8 * buf);
         }
-        ptx::fence_proxy_async_smem();
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(e2_tgt);
-      }
-      // ---------------- E3(t-2): D3 + bias -> fp32 [64, 8, 8] through a staged 16 KB bulk store
-      if (t >= 2) {
-        const long long q = ((long long)(t - 2) * p.nclusters + cluster_id) * 2 + rank;
-        ptx::mbar_wait(bar_m3_done, (uint32_t)((t - 2) & 1), 12, p.dbg);
-        ptx::tc_fence_after_sync();
-        if (etid == 0) ptx::tma_store_wait_read<0>();                 // the previous map's store has read the staging
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int m = wq * 32 + lane;
-        const int oy = m / kRow3, ox = m - oy * kRow3;
-        const bool valid = oy < 8 && ox < 8;
-        const uint32_t st = sm + oStage + (uint32_t)(oy * 8 + ox) * 4u;
+      } else {
+        // ---------------- E3(t-2): D3[(t-2) & 1] + bias -> fp32 [64, 8, 8] through a staged 16 KB bulk store
+        if (t >= 2) {
+          const int u = t - 2, buf = u & 1;
+          const long long q = ((long long)u * p.nclusters + cluster_id) * 2 + rank;
+          ptx::mbar_wait(bar_m3_done + 8 * buf, (uint32_t)((u >> 1) & 1), 12, p.dbg);
+          ptx::tc_fence_after_sync();
+          if (etid == 0) ptx::tma_store_wait_read<0>();               // the previous map's store has read the staging
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int m = wq * 32 + lane;
+          const int oy = m / kRow3, ox = m - oy * kRow3;
+          const bool valid = oy < 8 && ox < 8;
+          const uint32_t st = sm + oStage + (uint32_t)(oy * 8 + ox) * 4u;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(lane_t + kD3Col + h * 32, r);
-          ptx::tmem_ld_wait();
-          if (valid) {
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(lane_t + kD3Col + buf * kD3Cols + h * 32, r);
+            ptx::tmem_ld_wait();
+            if (valid) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              sts32f(st + (uint32_t)(h * 32 + c) * 256u, __uint_as_float(r[c]) + bias[48 + h * 32 + c]);
+              for (int c = 0; c < 32; ++c)
+                sts32f(st + (uint32_t)(h * 32 + c) * 256u, __uint_as_float(r[c]) + bias[48 + h * 32 + c]);
+            }
           }
-        }
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(e3_tgt);
-        ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (etid == 0 && q < p.nq) {
-          bulk_store_1d(p.out + q * 4096, sm + oStage, kStageBytes);
-          ptx::tma_store_commit();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(e3_tgt + 8 * buf);
+          ptx::fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (etid == 0 && q < p.nq) {
+            bulk_store_1d(p.out + q * 4096, sm + oStage, kStageBytes);
+            ptx::tma_store_commit();
+          }
         }
       }
     }
-    if (etid == 0) ptx::tma_store_wait_all<0>();
+    if (set_a && etid == 0) ptx::tma_store_wait_all<0>();
   }
 
   ptx::tc_fence_before_sync();

@@ -261,6 +261,30 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask
                : "memory");
 }
 
+// The same two operations for a CONVERGED warp: all 32 lanes execute the statement, one elected lane issues.
+// Keeping the issue loop warp-uniform lets ptxas emit `ELECT; @P UTCHMMA` with operands computed in the uniform
+// datapath, instead of the per-instruction election loop (ELECT / R2UR.BROADCAST x5 / BRA.U.ANY, ~15 issue slots)
+// it wraps around a tcgen05 instruction that sits in a divergent `if (lane == 0)` region — which matters when the
+// MMAs are short (N = 16..64: 8..32 cycles each).
+__device__ __forceinline__ void umma_f16_2cta_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                    uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta_elect(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
+
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (UMMA):
 //   rows of 128 B (64 bf16 of K), 8-row swizzle atoms 1024 B apart (SBO),
 //   version 1 (Blackwell), layout type 2 = SWIZZLE_128B.

@@ -85,8 +85,8 @@ class _Passthrough(torch.nn.Module):
 
     def forward(self, a, b, out_dict=None):
         if self.kind == "homo":
-            m = (a.mean(dim=(1, 2, 3)) - b.mean(dim=(1, 2, 3))).view(-1, 1)
-            return (torch.tanh(m) * torch.linspace(-6, 6, 8, device=a.device).view(1, 8)), None
+            # elementwise only: a reduction's summation order may depend on the batch size a replica sees
+            return torch.tanh(a[:, 0, 5, 3:11] - b[:, 1, 7, 2:10]) * 6.0, None
         lo = torch.nn.functional.avg_pool2d(a[:, :2] - b[:, :2], 8) * 0.02
         return [torch.nn.functional.interpolate(lo, size=a.shape[-2:], mode="bilinear", align_corners=True)]
 

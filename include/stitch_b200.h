@@ -74,6 +74,7 @@ enum {
   SB_TUNE_LOOKUP_PDL = 9,          /* r = 4 lookup launched with programmatic stream serialization (prologue overlaps the previous kernel's tail): 0 off, 1 on */
   SB_TUNE_CORR_A_TMEM = 10,        /* cost volume: 1 = the A block is copied to tensor memory once per unit and the MMAs read it from there */
   SB_TUNE_LOOKUP_GENERIC = 11,     /* EXPERIMENT: 1 = r = 4 lookups take the generic window-staging kernel (LDG.128) instead of the TMA-box kernel */
+  SB_TUNE_WARP_TILED = 12,         /* flow / homography warps: 1 = shared-memory-staged tiles where the shape allows (bit-identical, measured slower); default 0 = per-pixel gathers */
   SB_TUNE_COUNT = 16
 };
 int sb_tune(int key, int value);

@@ -20,6 +20,7 @@ namespace sb {
 struct GridTap {
   float nw, ne, sw, se;     // weights
   int off_nw;               // y_n * W + x_w (may be out of range; use masks)
+  int xi, yi;               // x_w, y_n saturated into [-2, W + 1] / [-2, H + 1] (NaN -> -2)
   bool m_nw, m_ne, m_sw, m_se;
 
   __device__ __forceinline__ void setup(float ix, float iy, int H, int W) {
@@ -30,8 +31,8 @@ struct GridTap {
     // Saturating float->int: anything outside [-1, size] is masked anyway.
     float xc = fminf(fmaxf(x_w, -2.0f), (float)W + 1.0f);
     float yc = fminf(fmaxf(y_n, -2.0f), (float)H + 1.0f);
-    int xi = (x_w == x_w) ? (int)xc : -2;   // NaN -> fully masked (weights stay NaN)
-    int yi = (y_n == y_n) ? (int)yc : -2;
+    xi = (x_w == x_w) ? (int)xc : -2;   // NaN -> fully masked (weights stay NaN)
+    yi = (y_n == y_n) ? (int)yc : -2;
     bool mw = (xi >= 0) & (xi < W), me = (xi + 1 >= 0) & (xi + 1 < W);
     bool mn = (yi >= 0) & (yi < H), ms = (yi + 1 >= 0) & (yi + 1 < H);
     m_nw = mn & mw; m_ne = mn & me; m_sw = ms & mw; m_se = ms & me;

@@ -393,6 +393,47 @@ def test_warp_edge_cases(sb):
         sb.warp(torch.zeros(1, 6, 8, 8, device="cuda"), torch.zeros(1, 2, 8, 9, device="cuda"))
 
 
+def test_tiled_warps_are_bit_identical_to_the_default_kernels(sb):
+    """The shared-memory-staged (TMA tile) forms of the flow and homography warps — opt-in through
+    sb_tune(SB_TUNE_WARP_TILED = 12, 1), measured slower than the per-pixel kernels — give the same bits: smooth and
+    noisy flows (outliers leave the staged box), non-finite flows, partial tiles, every channel count."""
+    lib = sb._lib.load()
+    g = torch.Generator().manual_seed(21)
+    cases_ = []
+    for (b, c, h, w) in ((2, 6, 72, 136), (1, 3, 40, 64), (1, 2, 128, 128), (1, 1, 24, 40), (2, 6, 512, 512)):
+        x = torch.rand(b, c, h, w, generator=g) * 255
+        smooth = torch.nn.functional.interpolate(torch.randn(b, 2, max(h // 8, 2), max(w // 8, 2), generator=g) * 3,
+                                                 size=(h, w), mode="bilinear", align_corners=True)
+        noisy = torch.randn(b, 2, h, w, generator=g) * 6
+        bad = smooth.clone()
+        for i, v in enumerate([float("nan"), float("inf"), -float("inf"), 1e30, -1e30, 3e9]):
+            bad[0, i % 2, 3 + i, 5 + 2 * i] = v
+        cases_.append((cu(x), [cu(smooth), cu(noisy), cu(bad), cu(smooth + 40.0)]))
+    src = torch.tensor([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]])
+    try:
+        for x, flows in cases_:
+            b, c, h, w = x.shape
+            mask = (torch.rand(b, 1, h, w, device="cuda") < 0.8).float()
+            thetas = [torch.eye(3, device="cuda")[None].repeat(b, 1, 1) + 0.05 * torch.randn(b, 3, 3, device="cuda") * s_
+                      for s_ in (0.2, 1.0, 4.0)]
+            outs = {}
+            for mode in (0, 1):
+                assert lib.sb_tune(12, mode) == 0
+                res = [sb.warp(x, f) for f in flows]
+                if c == 6:
+                    res += list(sb.warp(x, flows[0], mul_mask=mask, return_overlap=True))
+                for th in thetas:
+                    o, idx = sb.torch_homo_transform.transformer(x, th, (h + 7, w - 3), return_indices=True)
+                    res += [o, idx.float()]
+                    if c == 3:
+                        res.append(sb.torch_homo_transform.transformer(x, th, (h, w), append_ones=3))
+                outs[mode] = res
+            for a_, b_ in zip(outs[0], outs[1]):
+                assert_bits_equal(host(a_).view(np.uint32), host(b_).view(np.uint32), f"tiled vs per-pixel, shape {tuple(x.shape)}")
+    finally:
+        lib.sb_tune(12, 0)
+
+
 # ===================================================================== W2
 @pytest.mark.parametrize("name", ["homo_small", "homo_theta1", "homo_degenerate"])
 def test_homo_cases(sb, name):

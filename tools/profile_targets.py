@@ -27,6 +27,9 @@ tps_src = torch.stack([xs13, ys13], -1).reshape(1, -1, 2).repeat(B, 1, 1)
 tps_tgt = tps_src + 0.02 * rnd(B, 169, 2)
 k_src = tps_src * 0.48 + 0.5
 k_w, k_a = 0.01 * rnd(B, 169, 2), torch.tensor([[0.01, -0.02], [1.0, 0.01], [-0.01, 1.0]], device="cuda").repeat(B, 1, 1)
+gw = lambda o, c: ((torch.rand(o, c, 6, 6, device="cuda", generator=g) * 2 - 1) / (c * 36) ** 0.5, (torch.rand(o, device="cuda", generator=g) * 2 - 1) / (c * 36) ** 0.5)
+(pw1, pb1), (pw2, pb2), (pw3, pb3) = gw(16, 1), gw(32, 16), gw(64, 32)
+pe_pack = sb.encoder.pack_patch_embed_weights(pw1, pw2, pw3)
 for rep in range(2):
     if rep == 1:
         torch.cuda.synchronize()
@@ -35,6 +38,8 @@ for rep in range(2):
     vol, lv = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_levels=3)
     vol0 = C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64))
     tok = sb.encode_flow_token(vol.view(B * 4096, 1, 64, 64), coords)
+    pe = sb.encoder.patch_embed_proj(vol0.view(B * 4096, 1, 64, 64), pw1, pb1, pw2, pb2, pw3, pb3, pack=pe_pack)
+    del pe
     H, th, thi = sb.torch_DLT.dlt_thetas(src / 8, (src + 5.0) / 8, left=sb.torch_DLT._inv3(M), right=M)
     oh = sb.torch_homo_transform.transformer(img, th, (S, S), append_ones=3)
     o = sb.compute_occlusion(flo, flo, "wang", occlusion_are_zeros=True, threshold=True)

@@ -39,7 +39,7 @@ def launches():
 
 
 def full():
-    rep = os.path.join(src, "prof_r1.ncu-rep")
+    rep = os.path.join(src, f"prof_{tag}.ncu-rep")
     if not os.path.exists(rep):
         return
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -51,7 +51,10 @@ def full():
             "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
             "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-            "launch__registers_per_thread", "launch__grid_size", "smsp__inst_executed.sum"]
+            "launch__registers_per_thread", "launch__grid_size", "smsp__inst_executed.sum",
+            "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+            "smsp__inst_executed_pipe_uniform.sum", "sm__inst_executed_pipe_tc.sum",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg"]
 
     def to_bytes(v, u):
         v = float(v)
@@ -68,9 +71,9 @@ def full():
             rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
             wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
             f.write(f"| dram traffic (read+write) | {(rd+wr)/1e6:.1f} MB |\n\n")
-            if name.startswith("corr_umma_kernel<1>"):
+            if name.startswith("corr_umma_kernel<1>") or name.startswith("corr_umma_kernel<1,"):
                 json.dump({"kernel": name, "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
-                           "source": f"profiles/{tag}_ncu_full.md"}, open(os.path.join(OUT, "corr_umma_traffic.json"), "w"))
+                           "source": f"profiles/{tag}_ncu_full.md (ncu --set full --clock-control none, tools/profile_targets.py)"}, open(os.path.join(OUT, "corr_umma_traffic.json"), "w"))
     print("wrote", f"{tag}_ncu_full.md")
 
 

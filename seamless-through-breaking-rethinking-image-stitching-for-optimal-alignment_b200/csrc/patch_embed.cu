@@ -46,6 +46,9 @@ constexpr int kMB1 = 9, kMB2 = 3, kMB3 = 1;               // 128-row M blocks pe
 constexpr int kA1Entries = 1220;                           // 1 + 34 * 33 data, reads reach 9*128 - 1 + 66 + 2
 constexpr int kA1Bytes = kA1Entries * 16;                  // 19 520
 constexpr int kCh2 = 308, kCh3 = 92;                       // chunk strides (entries): 1 + 18*17 = 307, 1 + 10*9 = 91
+// (measured, round 2: strides 310 / 93 and 312 / 96 — which make the epilogue's 16-byte stores bank-conflict free —
+//  change nothing, and reading the biases as one LDS.128 batch per stage instead of per element made the kernel
+//  8 % slower (2.52 -> 2.73 ms): the epilogues are not what bounds it)
 constexpr int kA2Bytes = (8 * kCh2 + 112) * 16;            // + tail the last chunk's junk rows read (finite zeros)
 constexpr int kA3Bytes = (16 * kCh3 + 56) * 16;
 // ---- weights per CTA (half of the rows), K-major un-swizzled: [k/8][n/8][n%8][k%8]

@@ -113,6 +113,12 @@ flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flo,
 // 62.9 us (homography form: 55.8 vs 53.9 us).  The four phases of a CTA (flow load, bounding-box reduction, TMA
 // round trip, sampling) run back to back and 78 registers x 256 threads leave three CTAs per SM to overlap them.
 // Kept as an opt-in (sb_tune(SB_TUNE_WARP_TILED, 1)) with its tests; the per-pixel kernels stay the default.
+// Variants measured on the same workload (per-pixel kernel: 63.4 us): 64 x 16 tiles capped at 64 registers (four
+// CTAs per SM) 65.0 us; 32 x 16 tiles with 128 threads 72.7 - 81.0 us; 128 x 16 tiles 117.9 us.  ncu on the per-pixel
+// kernel: 76 % of the warp cycles wait on the L1TEX scoreboard (ptxas keeps it at 32 registers and consumes the 24
+// taps in small dependent batches), but neither issuing the 24 loads as ordered asm statements behind a warp-sync
+// fence (ptxas still interleaves them) nor an L1 prefetch (CCTL.PF1) per tap row ahead of the loads changes the
+// time (66.5 us; 138 us instead of 91 us for a noise flow), so both were dropped again.
 constexpr int kTW = 64, kTH = 16, kBoxW = 80, kBoxH = 25;
 constexpr int kPlaneFloats = (kBoxW * kBoxH + 31) / 32 * 32;   // 8000 B box, planes 8064 B apart: TMA destinations are 128-byte aligned
 

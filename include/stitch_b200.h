@@ -169,6 +169,10 @@ int sb_bilinear_sampler(const float* img, const float* coords, float* out,
  * of the UNMASKED warp (flowHomoAdpater.py:171-174 fused); NULL to skip. */
 int sb_flow_warp(const float* x, const float* flo, const float* mul_mask, float* out,
                  float* overlap, int B, int C, int H, int W, sb_stream_t stream);
+/* mode = 'nearest' of the same function (core/warp_utils.py:74-79 -> F.grid_sample(mode='nearest', zeros padding) — called
+ * WITHOUT align_corners there, i.e. align_corners=False): the pixel at the half-to-even rounded sample position, 0 outside. */
+int sb_flow_warp_nearest(const float* x, const float* flo, float* out, int B, int C, int H, int W,
+                         sb_stream_t stream);
 
 /* ------------------------------------------------------------------ W2
  * Replaces transformer(U, theta, out_size)

@@ -103,6 +103,29 @@ void o_flow_warp(const float* x, const float* flo, const float* mul_mask, float*
       }
 }
 
+/* W1, mode='nearest' — warp(x, flo, mode='nearest'): core/warp_utils.py:74-79.  The grid is normalised exactly as
+ * for the bilinear mode (2 v / max(size-1, 1) - 1), but the reference then calls F.grid_sample(mode='nearest') WITHOUT
+ * align_corners (:79), i.e. align_corners=False: ATen's CPU kernel un-normalises as fma(g + 1, size / 2, -0.5) (one
+ * rounding), rounds half to even (nearbyint) and copies that pixel if it lies inside the image, else 0. */
+void o_flow_warp_nearest(const float* x, const float* flo, float* out, int B, int C, int H, int W) {
+  const i64 plane = (i64)H * W;
+  const float denx = (float)(W - 1 > 1 ? W - 1 : 1), deny = (float)(H - 1 > 1 ? H - 1 : 1);
+  const float hw = (float)W / 2.0f, hh = (float)H / 2.0f;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int py = 0; py < H; ++py)
+      for (int px = 0; px < W; ++px) {
+        const i64 rem = (i64)py * W + px;
+        const float fx = flo[((i64)b * 2) * plane + rem], fy = flo[((i64)b * 2 + 1) * plane + rem];
+        const float gx = 2.0f * ((float)px + fx) / denx - 1.0f, gy = 2.0f * ((float)py + fy) / deny - 1.0f;
+        const float ix = nearbyintf(fmaf(gx + 1.0f, hw, -0.5f)), iy = nearbyintf(fmaf(gy + 1.0f, hh, -0.5f));
+        const int inside = ix >= 0.0f && ix <= (float)(W - 1) && iy >= 0.0f && iy <= (float)(H - 1);   /* false for NaN */
+        const i64 off = inside ? (i64)iy * W + (i64)ix : 0;
+        for (int c = 0; c < C; ++c)
+          out[((i64)b * C + c) * plane + rem] = inside ? x[((i64)b * C + c) * plane + off] : 0.0f;
+      }
+}
+
 /* bilinear_sampler(img, coords): core/utils/utils.py:62-76 */
 void o_bilinear_sampler(const float* img, const float* coords, float* out, int N, int C, int H,
                         int W, int Ho, int Wo) {

@@ -133,9 +133,14 @@ def bilinear_sampler(img, coords):
 
 
 # ----------------------------------------------------------------- W1
-def warp(x, flo, mul_mask=None, return_overlap=False):
+def warp(x, flo, mul_mask=None, return_overlap=False, mode="bilinear"):
     x, flo = _f32(x), _f32(flo)
     b, c, h, w = x.shape
+    if mode == "nearest":
+        assert mul_mask is None and not return_overlap
+        out = np.empty_like(x)
+        _load().o_flow_warp_nearest(_p(x), _p(flo), _p(out), c_int(b), c_int(c), c_int(h), c_int(w))
+        return out
     mm = None if mul_mask is None else _f32(mul_mask)
     out = np.empty_like(x)
     ov = np.empty((b, h, w), np.float32) if return_overlap else None

@@ -44,6 +44,7 @@ SIGNATURES = {
     "sb_corr_lookup": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, _P]),
     "sb_bilinear_sampler": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_flow_warp": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "sb_flow_warp_nearest": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_homo_warp": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_dlt_theta": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "sb_tps_warp": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -98,6 +98,35 @@ flow_warp_kernel(const float* __restrict__ x, const float* __restrict__ flo,
   }
 }
 
+// mode = 'nearest' of the reference's warp (core/warp_utils.py:74-79).  The grid is normalised as for the bilinear mode
+// (2 v / max(size-1, 1) - 1) but the reference then calls F.grid_sample(mode='nearest') WITHOUT align_corners (:79), i.e.
+// align_corners=False: ATen's CPU kernel un-normalises as fma(g + 1, size / 2, -0.5) (one rounding), rounds half to even
+// (nearbyint) and copies that pixel if it lies inside the image, else 0.  No caller in the reference uses this mode; it
+// exists so that the mirrored signature is complete.
+__global__ void __launch_bounds__(256)
+flow_warp_nearest_kernel(const float* __restrict__ x, const float* __restrict__ flo, float* __restrict__ out, int C,
+                         int H, int W, const FlowWarpConst k) {
+  const int px = blockIdx.x * 32 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
+  if (px >= W || py >= H) return;
+  const int b = blockIdx.z;
+  const int plane = H * W;
+  const int rem = py * W + px;
+  const float* fl = flo + (size_t)b * 2 * plane + rem;
+  const float fx = ldg_stream(fl), fy = ldg_stream(fl + plane);
+  const float gx = fsub(fdiv(fmul(2.0f, fadd((float)px, fx)), k.denx), 1.0f);
+  const float gy = fsub(fdiv(fmul(2.0f, fadd((float)py, fy)), k.deny), 1.0f);
+  const float ix = nearbyintf(__fmaf_rn(fadd(gx, 1.0f), fmul((float)W, 0.5f), -0.5f));      // round half to even
+  const float iy = nearbyintf(__fmaf_rn(fadd(gy, 1.0f), fmul((float)H, 0.5f), -0.5f));
+  const bool inside = ix >= 0.0f && ix <= (float)(W - 1) && iy >= 0.0f && iy <= (float)(H - 1);   // false for NaN
+  const size_t off = inside ? (size_t)((int)iy) * W + (int)ix : 0;
+  const float* src = x + (size_t)b * C * plane + off;
+  float* po = out + (size_t)b * C * plane + rem;
+  for (int c = 0; c < C; ++c) {
+    stg_stream(po, inside ? __ldg(src) : 0.0f);
+    src += plane; po += plane;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Tiled form (W % 4 == 0, C in {1, 2, 3, 6}): shared-memory staging of the source tile.
 // The per-pixel kernel above is bound by the L1 data stage, not by HBM or issue slots: 24 four-byte gathers per
@@ -250,6 +279,25 @@ static int launch_flow_tiled(const float* x, const float* flo, const float* mul_
 }
 
 }  // namespace sb
+
+extern "C" int sb_flow_warp_nearest(const float* x, const float* flo, float* out, int B, int C, int H, int W,
+                                    sb_stream_t stream) {
+  using namespace sb;
+  SB_ENTER();
+  SB_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, SB_EINVAL, "sb_flow_warp_nearest: negative size");
+  SB_REQUIRE((long long)H * W < (1ll << 31), SB_EUNSUP, "sb_flow_warp_nearest: plane too large");
+  if ((long long)B * H * W == 0 || C == 0) return SB_OK;
+  SB_REQUIRE(x && flo && out, SB_EINVAL, "sb_flow_warp_nearest: null pointer");
+  SB_REQUIRE(B <= 65535 && (H + 7) / 8 <= 65535, SB_EUNSUP, "sb_flow_warp_nearest: B or H too large for one launch");
+  const dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, B);
+  FlowWarpConst k;
+  k.denx = (float)(W - 1 > 1 ? W - 1 : 1); k.deny = (float)(H - 1 > 1 ? H - 1 : 1);
+  k.rcpx = 1.0f / k.denx; k.rcpy = 1.0f / k.deny;
+  k.halfx = (float)(W - 1) * 0.5f; k.halfy = (float)(H - 1) * 0.5f;
+  flow_warp_nearest_kernel<<<grid, block, 0, as_stream(stream)>>>(x, flo, out, C, H, W, k);
+  SB_LAUNCH_CHECK("flow_warp_nearest_kernel");
+  return SB_OK;
+}
 
 extern "C" int sb_flow_warp(const float* x, const float* flo, const float* mul_mask, float* out,
                             float* overlap, int B, int C, int H, int W, sb_stream_t stream) {

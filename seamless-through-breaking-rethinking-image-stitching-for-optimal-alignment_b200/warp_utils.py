@@ -83,13 +83,28 @@ def mask_invalid(coords, pad_h=0, pad_w=0):
 def warp(x, flo, mode="bilinear", mul_mask=None, return_overlap=False):
     """Backward warp of ``x [B,C,H,W]`` by ``flo [B,2,H,W]`` (warp_utils.py:71-80).
 
+    ``mode='nearest'`` follows the reference to the letter: its non-bilinear branch calls ``F.grid_sample`` without
+    ``align_corners`` (:79), so the nearest mode samples with ``align_corners=False``.
+
     ``mul_mask`` ([B,1,H,W], optional, not in the reference signature) fuses the
     caller's ``final_warp_output * mask`` (flowHomoAdpater.py:182,317) into the
     same pass; ``return_overlap=True`` (C == 6) also returns
     ``where(mean(out[:,3:6]) < 0.9, 1, 0)`` of the unmasked warp (:171-174)."""
-    if mode != "bilinear":
-        raise NotImplementedError("warp: only the bilinear mode of the reference's call sites is implemented")
+    if mode not in ("bilinear", "nearest"):
+        raise ValueError(f"warp: mode must be 'bilinear' or 'nearest' (F.grid_sample's modes the reference passes on), got {mode!r}")
     lib = _lib.load()
+    if mode == "nearest":
+        if mul_mask is not None or return_overlap:
+            raise ValueError("warp: mul_mask / return_overlap are extensions of the bilinear mode")
+        xs = _lib.dev_f32(x, "x")
+        fl = _lib.dev_f32(flo, "flo")
+        if xs.dim() != 4 or fl.dim() != 4 or fl.shape[1] != 2 or xs.shape[0] != fl.shape[0] or xs.shape[2:] != fl.shape[2:]:
+            raise ValueError(f"warp: x {tuple(xs.shape)} and flo {tuple(fl.shape)} do not match")
+        b, c, h, w = xs.shape
+        out = torch.empty_like(xs)
+        _lib.check(lib.sb_flow_warp_nearest(_lib.ptr(xs), _lib.ptr(fl), _lib.ptr(out), b, c, h, w, _lib.stream_ptr()),
+                   "sb_flow_warp_nearest")
+        return out
     xs = _lib.dev_f32(x, "x")
     fl = _lib.dev_f32(flo, "flo")
     if xs.dim() != 4 or fl.dim() != 4 or fl.shape[1] != 2 or xs.shape[0] != fl.shape[0] or xs.shape[2:] != fl.shape[2:]:

@@ -143,7 +143,8 @@ def main():
     # ---------------------------------------------------------------- W1
     for name, fn in (("warp_small", cases.warp_small), ("warp_flow2", cases.warp_flow2)):
         c = fn()
-        save(name, cases.checksum(*c.values()), out=ref_wu.warp(c["x"], c["flo"]).numpy())
+        save(name, cases.checksum(*c.values()), out=ref_wu.warp(c["x"], c["flo"]).numpy(),
+             out_nearest=ref_wu.warp(c["x"], c["flo"], mode="nearest").numpy())
     c = cases.warp_512()
     out = ref_wu.warp(c["x"], c["flo"])
     save("warp_512", cases.checksum(*c.values()), out_sample=out[..., cases.WARP_512_SAMPLE[0], cases.WARP_512_SAMPLE[1]].numpy())

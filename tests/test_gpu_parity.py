@@ -354,6 +354,12 @@ def test_warp_cases(sb, name):
     out = host(sb.warp(cu(c["x"]), cu(c["flo"])))
     assert max_abs(out, g["out"]) <= 1e-3                     # the contract
     assert_bits_equal(out, g["out"], "warp vs reference golden")   # and in fact bit-exact
+    # mode='nearest' (core/warp_utils.py:76-77; no caller in the reference, part of the mirrored signature)
+    near = host(sb.warp(cu(c["x"]), cu(c["flo"]), mode="nearest"))
+    assert_bits_equal(near, g["out_nearest"], "nearest-mode warp vs reference golden")
+    assert_bits_equal(near, so.warp(c["x"].numpy(), c["flo"].numpy(), mode="nearest"), "nearest-mode warp vs oracle")
+    with pytest.raises(ValueError, match="mode"):
+        sb.warp(cu(c["x"]), cu(c["flo"]), mode="bicubic")
 
 
 def test_warp_512_golden(sb):

@@ -75,6 +75,8 @@ def test_warp(name):
     out = so.warp(c["x"].numpy(), c["flo"].numpy())
     # contract: 1e-3 max-abs on 0..255 images; the restated arithmetic is bit-exact
     assert_bits_equal(out, g["out"], "warp")
+    # mode='nearest' (warp_utils.py:76-77 -> grid_sample nearest, half-to-even rounding, zeros outside)
+    assert_bits_equal(so.warp(c["x"].numpy(), c["flo"].numpy(), mode="nearest"), g["out_nearest"], "warp, nearest")
 
 
 def test_warp_512():

@@ -121,14 +121,14 @@ def main():
     @torch.no_grad()
     def one_step():
         keep = []
-        for (fa, fb), c0 in (((pb.fmap1, pb.fmap2), 0), ((pb.fmap2, pb.fmap1), args.iters)):
+        for (fa, fb), d in (((pb.fmap1, pb.fmap2), 0), ((pb.fmap2, pb.fmap1), 1)):
             vol = MemoryEncoder.corr(enc_self, fa, fb)
             cost_maps = vol.permute(0, 2, 3, 1, 4, 5).contiguous().view(b * s8 * s8, 1, s8, s8)      # encoder.py:260
             l1 = F.avg_pool2d(cost_maps, 2, stride=2)
             l2 = F.avg_pool2d(l1, 2, stride=2)
             l3 = F.avg_pool2d(l2, 2, stride=2)
             for it in range(args.iters):
-                keep.append(MemoryDecoder.encode_flow_token(None, cost_maps, pb.coords[c0 + it]))
+                keep.append(MemoryDecoder.encode_flow_token(None, cost_maps, pb.coords[it, d]))
             keep.append(l3)
         adapter.flow_backbone.calls = 0
         out = adapter.train_eval_foward(pb.image1, pb.image2)

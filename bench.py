@@ -116,10 +116,10 @@ def cpu_pairs_per_s(n_pairs, min_seconds, max_seconds=60.0):
 
     def one_pass():
         b = n_pairs
-        for f1, f2 in ((a["fmap1"], a["fmap2"]), (a["fmap2"], a["fmap1"])):
+        for d, (f1, f2) in enumerate(((a["fmap1"], a["fmap2"]), (a["fmap2"], a["fmap1"]))):
             pyr = so.corr_pyramid(f1, f2, 4)
             for it in range(ITERS):
-                so.encode_flow_token(pyr[0], a["coords"][it])
+                so.encode_flow_token(pyr[0], a["coords"][it, d])
         src = np.tile(np.array([[0.0, 0.0], [SIZE, 0.0], [0.0, SIZE], [SIZE, SIZE]], np.float32)[None], (b, 1, 1))
         H = so.tensor_DLT(src / 8, (src + a["h_motion"]) / 8)
         M = np.array([[SIZE / 16.0, 0, SIZE / 16.0], [0, SIZE / 16.0, SIZE / 16.0], [0, 0, 1]], np.float32)
@@ -262,7 +262,7 @@ def run_ours(args):
         (lambda t: _lib.pinned_like(t, write_combined=True)) if args.wc else (lambda t: t.pin_memory()))
     pb_dev = pb_host.map(lambda t: t.to(dev, non_blocking=True))
     hp = HotPath(size=SIZE, iters=ITERS, pyramid=True, overlap=args.overlap, eval_outputs=not args.graph,
-                 lookup_subbatch=args.lookup_subbatch)
+                 lookup_subbatch=args.lookup_subbatch, bidirectional=args.bidirectional)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -310,15 +310,22 @@ def run_ours(args):
         launches = launches_per_step_eager * args.steps
         from stitch_b200 import corr as corr_mod
         s8 = SIZE // 8
-        tk1, tk2 = corr_mod.tokens_bf16(pb_dev.fmap1), corr_mod.tokens_bf16(pb_dev.fmap2)
-        for _ in range(3):
-            corr_mod.corr_from_tokens(tk1, tk2, 256, (s8, s8), (s8, s8), pyramid_levels=3)
         n_rep = 20
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_rep + 1)]
+        if args.bidirectional:
+            # the launch the step makes: forward and backward volumes of the batch in one launch (2B batch elements)
+            tk = torch.empty((2 * B, s8 * s8, 256), dtype=torch.bfloat16, device=dev)
+            corr_mod.tokens_bf16(pb_dev.fmap1, out=tk[:B]); corr_mod.tokens_bf16(pb_dev.fmap2, out=tk[B:])
+            launch = lambda i: corr_mod.corr_bidirectional_from_tokens(tk, 256, (s8, s8), pyramid_levels=3)
+        else:
+            tk1, tk2 = corr_mod.tokens_bf16(pb_dev.fmap1), corr_mod.tokens_bf16(pb_dev.fmap2)
+            launch = lambda i: corr_mod.corr_from_tokens(tk1 if i % 2 == 0 else tk2, tk2 if i % 2 == 0 else tk1, 256,
+                                                         (s8, s8), (s8, s8), pyramid_levels=3)
+        for i in range(3):
+            launch(i)
         evs[0].record(stream)
         for i in range(n_rep):
-            corr_mod.corr_from_tokens(tk1 if i % 2 == 0 else tk2, tk2 if i % 2 == 0 else tk1, 256, (s8, s8), (s8, s8),
-                                      pyramid_levels=3)
+            launch(i)
             evs[i + 1].record(stream)
         barrier()
         gemm_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(n_rep)]
@@ -435,16 +442,18 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        # dominant kernel: corr_umma_kernel. Algorithmic bytes per launch = one direction of the batch:
-        # B * (N1*N2*4 * (1 + 1/4 + 1/16 + 1/64) written + (N1+N2)*C*2 bf16 operands read)
+        # dominant kernel: corr_umma_kernel. One launch = one direction of the batch (B volumes; 2B with --bidirectional):
+        # algorithmic bytes per launch = vols * (N1*N2*4 * (1 + 1/4 + 1/16 + 1/64) written + (N1+N2)*C*2 bf16 operands read)
         n = (SIZE // 8) ** 2
-        gemm_bytes = B * (n * n * 4 * (1 + 0.25 + 0.0625 + 0.015625) + 2 * n * 256 * 2)
-        gemm_flops = B * 2.0 * n * n * 256
+        vols = (2 * B) if (args.bidirectional and args.graph) else B
+        gemm_bytes = vols * (n * n * 4 * (1 + 0.25 + 0.0625 + 0.015625) + 2 * n * 256 * 2)
+        gemm_flops = vols * 2.0 * n * n * 256
         gemm_avg_ms = statistics.mean(gemm_ms) if gemm_ms else float("nan")
         achieved = gemm_bytes / (gemm_avg_ms / 1000.0) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "corr_umma_traffic.json")))["dram_bytes_per_launch"]
+            # the ncu capture is a 16-volume launch; DRAM bytes scale with the number of volumes a launch writes
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "corr_umma_traffic.json")))["dram_bytes_per_launch"] / 16.0 * vols
         except Exception:
             pass
         cpu = None
@@ -464,13 +473,15 @@ def run_ours(args):
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic,
                          "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture "
-                                           "of this kernel at this shape (profiles/corr_umma_traffic.json); not re-measured in this run",
+                                           "of this kernel on 16 volumes of this shape (profiles/corr_umma_traffic.json), scaled to volumes_per_launch; "
+                                           "not re-measured in this run",
                          "peak_source": peak_src, "avg_launch_ms": gemm_avg_ms,
                          "launches_timed": len(gemm_ms), "algorithmic_bytes_per_launch": gemm_bytes,
                          "tensor_tflops": gemm_flops / (gemm_avg_ms / 1000.0) / 1e12,
                          "tensor_frac_of_sustained": (gemm_flops / (gemm_avg_ms / 1000.0) / 1e12) /
                          float(peaks.get("bf16_tflops_sustained", 1400.0)),
-                         "kernel_share_of_step": (2 * gemm_avg_ms / (ms_max / args.steps)) if gemm_ms else None,
+                         "kernel_share_of_step": ((2 * B // vols) * gemm_avg_ms / (ms_max / args.steps)) if gemm_ms else None,
+                         "volumes_per_launch": vols,
                          "timed": ("CUDA events around 20 back-to-back launches on the launching stream right after the "
                                    "graph-replay region (events cannot be timed inside a captured graph)") if args.graph
                          else "CUDA events around every launch inside the timed region (eager)"},
@@ -508,6 +519,8 @@ def main():
     ap.add_argument("--lookup-subbatch", type=int, default=0,
                     help="run the 12 lookups of a direction per sub-batch of this many pairs (L2 residency experiment; "
                          "0 = one lookup per iteration over the whole batch, as the decoder issues them)")
+    ap.add_argument("--bidirectional", action="store_true",
+                    help="forward and backward direction of the batch as one launch each (experiment; measured slower)")
     ap.add_argument("--wc", action="store_true", help="write-combined pinned host input buffers (experiment)")
     ap.set_defaults(graph=True, overlap=True)
     args = ap.parse_args()

@@ -75,6 +75,7 @@ enum {
   SB_TUNE_CORR_A_TMEM = 10,        /* cost volume: 1 = the A block is copied to tensor memory once per unit and the MMAs read it from there */
   SB_TUNE_LOOKUP_GENERIC = 11,     /* EXPERIMENT: 1 = r = 4 lookups take the generic window-staging kernel (LDG.128) instead of the TMA-box kernel */
   SB_TUNE_WARP_TILED = 12,         /* flow / homography warps: 1 = shared-memory-staged tiles where the shape allows (bit-identical, measured slower); default 0 = per-pixel gathers */
+  SB_TUNE_CORR_TILES_PER_UNIT = 13, /* cost volume: target tiles per work unit (the A block is loaded once per unit): 4 (default), 8 or 16 */
   SB_TUNE_COUNT = 16
 };
 int sb_tune(int key, int value);
@@ -115,6 +116,11 @@ int sb_feat_to_tokens_bf16(const float* fmap, void* tok, int B, int C, int N,
 int sb_corr_tokens(const void* tok1, const void* tok2, float* vol,
                    float* lvl1, float* lvl2, float* lvl3,
                    int B, int C, int H1, int W1, int H2, int W2, sb_stream_t stream);
+/* Forward AND backward volume of Bp pairs in one launch (the two FlowFormer calls of flowHomoAdpater.py:158,178
+ * share their inputs): tok_both [2*Bp, N, Cpad] bf16 = image-1 maps then image-2 maps; vol [2*Bp, N, N] (and the
+ * levels) hold corr(img1_b, img2_b) for b < Bp and corr(img2_b, img1_b) for Bp + b.  H1 = H2 = H, W1 = W2 = W. */
+int sb_corr_tokens_bidir(const void* tok_both, float* vol, float* lvl1, float* lvl2, float* lvl3,
+                         int Bp, int C, int H, int W, sb_stream_t stream);
 /* Opt-in (not the reference's dtype): the volume written as bf16 [B, N1, N2], H2*W2 % 8 == 0 — half
  * the HBM bytes, which moves the kernel from the write roofline towards the tensor pipe. */
 int sb_corr_tokens_bf16out(const void* tok1, const void* tok2, void* vol_bf16,

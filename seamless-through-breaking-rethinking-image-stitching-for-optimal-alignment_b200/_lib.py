@@ -37,6 +37,7 @@ SIGNATURES = {
     "sb_corr": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_feat_to_tokens_bf16": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "sb_corr_tokens": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sb_corr_tokens_bidir": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_attn_softmax_tokens": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sb_corr_tokens_pitched": (c_int, [_P, _P, _P, c_longlong, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sb_corr_tokens_bf16out": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["corr", "corr_pyramid", "memory_encoder_corr", "tokens_bf16", "corr_from_tokens"]
+__all__ = ["corr_bidirectional", "corr_bidirectional_from_tokens", "corr", "corr_pyramid", "memory_encoder_corr", "tokens_bf16", "corr_from_tokens"]
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
@@ -100,15 +100,18 @@ def memory_encoder_corr(self, fmap1, fmap2):
     return corr(fmap1, fmap2, heads=int(self.cfg.cost_heads_num))
 
 
-def tokens_bf16(fmap: torch.Tensor) -> torch.Tensor:
+def tokens_bf16(fmap: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     """fp32 ``[B,C,H,W]`` -> bf16 token-major ``[B, H*W, Cpad]`` (the MMA operand
     layout). Lets a caller convert each image's features once and build both the
-    forward and the backward volume from them."""
+    forward and the backward volume from them.  ``out``: a dense bf16 ``[B, H*W, Cpad]`` buffer to fill."""
     lib = _lib.load()
     f = _lib.dev_f32(fmap, "fmap")
     b, c, h, w = f.shape
     cpad = (c + 63) // 64 * 64
-    tok = torch.empty((b, h * w, cpad), dtype=torch.bfloat16, device=f.device)
+    if out is not None:
+        if tuple(out.shape) != (b, h * w, cpad) or out.dtype != torch.bfloat16 or not out.is_contiguous() or out.device != f.device:
+            raise ValueError(f"tokens_bf16: out must be a dense bf16 [{b},{h * w},{cpad}] tensor on {f.device}")
+    tok = out if out is not None else torch.empty((b, h * w, cpad), dtype=torch.bfloat16, device=f.device)
     _lib.check(lib.sb_feat_to_tokens_bf16(_lib.ptr(f), _lib.ptr(tok), b, c, h * w, _lib.stream_ptr()),
                "sb_feat_to_tokens_bf16")
     return tok
@@ -140,6 +143,49 @@ def corr_from_tokens(tok1: torch.Tensor, tok2: torch.Tensor, c: int, hw1, hw2, p
                             _lib.ptr(lv[2]), b, c, h1, w1, h2, w2, _lib.stream_ptr())
     _lib.check(rc, "sb_corr_tokens")
     out = vol.view(b, 1, h1, w1, h2, w2)
+    return (out, lv[:pyramid_levels]) if pyramid_levels else out
+
+
+def corr_bidirectional(fmap1: torch.Tensor, fmap2: torch.Tensor, pyramid_levels: int = 0):
+    """Forward and backward cost volume of a batch of pairs in ONE launch (heads = 1, equal map sizes).
+
+    The reference builds them in two FlowFormer calls with swapped inputs (``flowHomoAdpater.py:158,178``); both need
+    the same two feature maps.  Returns ``vol [2B,1,H,W,H,W]`` — ``vol[:B] == corr(fmap1, fmap2)``,
+    ``vol[B:] == corr(fmap2, fmap1)`` bit for bit — and, with ``pyramid_levels``, the pooled levels ``[2B*H*W,1,h,w]``."""
+    lib = _lib.load()
+    f1 = _lib.dev_f32(fmap1, "fmap1")
+    f2 = _lib.dev_f32(fmap2, "fmap2")
+    if f1.dim() != 4 or f1.shape != f2.shape:
+        raise ValueError(f"corr_bidirectional: expected two [B,C,H,W] feature maps of equal shape; got {tuple(f1.shape)} {tuple(f2.shape)}")
+    if not 0 <= pyramid_levels <= 3:
+        raise ValueError("pyramid_levels must be in 0..3")
+    b, c, h, w = f1.shape
+    n = h * w
+    if n % 4:
+        raise ValueError("corr_bidirectional: H*W must be a multiple of 4 (use corr() for ragged maps)")
+    cpad = (c + 63) // 64 * 64
+    tok = torch.empty((2 * b, n, cpad), dtype=torch.bfloat16, device=f1.device)
+    tokens_bf16(f1, out=tok[:b])
+    tokens_bf16(f2, out=tok[b:])
+    return corr_bidirectional_from_tokens(tok, c, (h, w), pyramid_levels)
+
+
+def corr_bidirectional_from_tokens(tok_both: torch.Tensor, c: int, hw, pyramid_levels: int = 0):
+    """:func:`corr_bidirectional` from ``tok_both [2B, H*W, Cpad]`` (image-1 token maps, then image-2's)."""
+    lib = _lib.load()
+    h, w = hw
+    n = h * w
+    if tok_both.dtype != torch.bfloat16 or not tok_both.is_cuda or tok_both.dim() != 3 or tok_both.shape[0] % 2 or tok_both.shape[1] != n:
+        raise RuntimeError("corr_bidirectional_from_tokens: expected a CUDA bf16 [2B, H*W, Cpad] token tensor")
+    b = tok_both.shape[0] // 2
+    vol = torch.empty((2 * b, n, n), dtype=torch.float32, device=tok_both.device)
+    lv = [None, None, None]
+    for l in range(pyramid_levels):
+        lv[l] = torch.empty((2 * b * n, 1, h >> (l + 1), w >> (l + 1)), dtype=torch.float32, device=tok_both.device)
+    if b * n > 0:
+        _lib.check(lib.sb_corr_tokens_bidir(_lib.ptr(tok_both), _lib.ptr(vol), _lib.ptr(lv[0]), _lib.ptr(lv[1]), _lib.ptr(lv[2]),
+                                            b, c, h, w, _lib.stream_ptr()), "sb_corr_tokens_bidir")
+    out = vol.view(2 * b, 1, h, w, h, w)
     return (out, lv[:pyramid_levels]) if pyramid_levels else out
 
 

@@ -121,6 +121,7 @@ struct CorrParams {
   int store_policy;             // L2 policy of the output stores (sb_tune SB_TUNE_CORR_STORE_POLICY)
   int tpu;                      // tiles per unit (kTilesPerUnit; 8 for POOL == 2; NT for the softmax statistics pass)
   float* smx;                   // SMX: per-row (max, sum of exp) [B, N1, 2]; written by pass 1, read by pass 2
+  int b_rot;                    // the B operand of batch element b is token map (b + b_rot) mod B (0: the same index)
 };
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
@@ -261,6 +262,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         a_par ^= 1;
         const int t0 = ng * p.tpu;
         const int t1 = min(t0 + p.tpu, p.NT);
+        const int bb = (b + p.b_rot >= p.B) ? b + p.b_rot - p.B : b + p.b_rot;     // batch element of the B operand
         for (int t = t0; t < t1; ++t) {
           ptx::mbar_wait(bar_b_empty + 8 * stage, b_par ^ 1, 2, p.dbg);
           if (!TWO_CTA) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, b_tx);
@@ -268,9 +270,9 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t b_full_tgt = TWO_CTA ? ptx::mapa_shared(bar_b_full + 8 * stage, 0) : bar_b_full + 8 * stage;
           for (int kp = 0; kp < p.KP; ++kp) {
             const uint32_t dstb = sB + (stage * kMaxPanels + kp) * kBPanelBytes;
-            if (TWO_CTA) ptx::tma_load_3d_2cta(dstb, &map_b, b_full_tgt, kp * BKP, t * BN + (int)cta_rank * kBRows, b);
-            else if (ld_policy) ptx::tma_load_3d_hint(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, b, ld_policy);
-            else ptx::tma_load_3d(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, b);
+            if (TWO_CTA) ptx::tma_load_3d_2cta(dstb, &map_b, b_full_tgt, kp * BKP, t * BN + (int)cta_rank * kBRows, bb);
+            else if (ld_policy) ptx::tma_load_3d_hint(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, bb, ld_policy);
+            else ptx::tma_load_3d(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, bb);
           }
           if (++stage == kStages) { stage = 0; b_par ^= 1; }
         }
@@ -530,9 +532,11 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         (void)g2a;
         continue;
       }
+      // a unit is p.tpu tiles (a multiple of 4 when pooling): the pooling state closes every 4 tiles, the A block stays
+      for (int tb = t0; tb < t1; tb += kTilesPerUnit) {
 #pragma unroll
       for (int tt = 0; tt < kTilesPerUnit; ++tt) {
-        const int t = t0 + tt;
+        const int t = tb + tt;
         if (t >= t1) break;
         ptx::mbar_wait(bar_t_full + 8 * acc, acc_par, 6, p.dbg);
         ptx::tc_fence_after_sync();
@@ -710,6 +714,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
       }
+      }
     }
     if (lane == 0) ptx::tma_store_wait_all<0>();
   }
@@ -816,13 +821,22 @@ extern "C" int sb_corr_tokens(const void* tok1, const void* tok2, float* vol, fl
 namespace sb {
 static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, long long vol_pitch, bool bf16_out,
                             float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1, int H2, int W2,
-                            sb_stream_t stream, float* smx_stats = nullptr);
+                            sb_stream_t stream, float* smx_stats = nullptr, int b_rot = 0);
 }
 
 extern "C" int sb_corr_tokens_pitched(const void* tok1, const void* tok2, float* vol, long long vol_pitch,
                                       float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1,
                                       int H2, int W2, sb_stream_t stream) {
   return sb::corr_tokens_impl(tok1, tok2, vol, vol_pitch, false, lvl1, lvl2, lvl3, B, C, H1, W1, H2, W2, stream);
+}
+
+// Both directions of a batch of pairs in ONE launch: tok_both [2 * Bp, N, Cpad] = the token maps of image 1 of every
+// pair followed by those of image 2; volume element b < Bp is corr(img1_b, img2_b) (forward), element Bp + b is
+// corr(img2_b, img1_b) (backward): the B operand of batch element b is token map (b + Bp) mod 2 Bp.
+extern "C" int sb_corr_tokens_bidir(const void* tok_both, float* vol, float* lvl1, float* lvl2, float* lvl3, int Bp,
+                                    int C, int H, int W, sb_stream_t stream) {
+  return sb::corr_tokens_impl(tok_both, tok_both, vol, (long long)H * W, false, lvl1, lvl2, lvl3, 2 * Bp, C, H, W, H, W,
+                              stream, nullptr, Bp);
 }
 
 // softmax over the keys of q . k^T, TF32-rounded probabilities [B, Nq, Nk] (GMA Attention.forward);
@@ -844,7 +858,7 @@ extern "C" int sb_corr_tokens_bf16out(const void* tok1, const void* tok2, void* 
 namespace sb {
 static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, long long vol_pitch, bool bf16_out,
                             float* lvl1, float* lvl2, float* lvl3, int B, int C, int H1, int W1, int H2, int W2,
-                            sb_stream_t stream, float* smx_stats) {
+                            sb_stream_t stream, float* smx_stats, int b_rot) {
   float* vol = static_cast<float*>(vol_any);
   SB_ENTER();
   SB_REQUIRE(tok1 && tok2 && vol, SB_EINVAL, "sb_corr_tokens: null pointer");
@@ -911,14 +925,19 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     return SB_ECUDA;
   }
 
+  const bool a_tmem_req = tune_get(SB_TUNE_CORR_A_TMEM, 0) == 1 && !two_cta && !bf16_out && !smx_stats && pool_mode != 2;
   CorrParams p;
   p.B = B; p.N1 = (int)N1; p.N2 = (int)N2; p.KP = Cpad / 64;
   p.MB = (int)((N1 + BM - 1) / BM);
   if (two_cta) p.MB = (p.MB + 1) / 2;             // units are pairs of query blocks
   p.NT = (int)((N2 + BN - 1) / BN);
-  const int tpu = (pool_mode == 2) ? 8 : kTilesPerUnit;
+  // tiles per unit: 4 (default) keeps A for 4 B tiles; SB_TUNE_CORR_TILES_PER_UNIT = 8 / 16 halves / quarters the A reloads
+  int tpu_tune = tune_get(SB_TUNE_CORR_TILES_PER_UNIT, kTilesPerUnit);
+  if (tpu_tune != 8 && tpu_tune != 16) tpu_tune = kTilesPerUnit;
+  const int tpu = (pool_mode == 2) ? 8 : ((two_cta || a_tmem_req) ? kTilesPerUnit : tpu_tune);
   p.tpu = tpu;
   p.smx = smx_stats;
+  p.b_rot = (B > 0) ? ((b_rot % B) + B) % B : 0;
   p.NG = (p.NT + tpu - 1) / tpu;
   p.n_units = (long long)B * p.MB * p.NG;
   p.H2h = H2 / 2; p.H2q = H2 / 4; p.H2e = H2 / 8;
@@ -931,7 +950,7 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     p.store_policy = ((tp & 3) == 3 ? 0 : (tp & 3)) | (tp & 4);
   }
 
-  const bool a_tmem = tune_get(SB_TUNE_CORR_A_TMEM, 0) == 1 && !two_cta && !bf16_out && !smx_stats && pool_mode != 2;
+  const bool a_tmem = a_tmem_req;
   const int grid = (int)((p.n_units < kNumSMs) ? p.n_units : kNumSMs);
   static SmemOptIn opt_in;
   int opt_dev;

@@ -226,6 +226,43 @@ def test_corr_full_batch_properties(sb):
     assert torch.equal(vol2, vol)
 
 
+def test_corr_bidirectional_is_both_volumes_bit_for_bit(sb):
+    """Forward and backward volume (+ fused pyramid) of a batch of pairs from ONE launch == the two separate launches."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for (b, c, h, w, lv) in ((3, 256, 64, 64, 3), (2, 96, 16, 24, 0), (1, 256, 64, 64, 0), (5, 64, 8, 16, 3)):
+        f1 = torch.randn(b, c, h, w, device="cuda", generator=g)
+        f2 = torch.randn(b, c, h, w, device="cuda", generator=g)
+        res = sb.corr.corr_bidirectional(f1, f2, pyramid_levels=lv)
+        fwd = sb.corr.corr(f1, f2, pyramid_levels=lv)
+        bwd = sb.corr.corr(f2, f1, pyramid_levels=lv)
+        vol = res[0] if lv else res
+        vf, vb = (fwd[0], bwd[0]) if lv else (fwd, bwd)
+        assert vol.shape == (2 * b, 1, h, w, h, w)
+        assert torch.equal(vol[:b], vf) and torch.equal(vol[b:], vb)
+        for l in range(lv):
+            both = res[1][l].view(2, -1)
+            assert torch.equal(both[0], fwd[1][l].view(-1)) and torch.equal(both[1], bwd[1][l].view(-1))
+    with pytest.raises(ValueError):
+        sb.corr.corr_bidirectional(torch.zeros(1, 64, 8, 8, device="cuda"), torch.zeros(1, 64, 8, 16, device="cuda"))
+
+
+def test_step_bidirectional_equals_two_directions(sb):
+    """HotPath with the two directions batched into one launch each (21 launches) == the per-direction step (34)."""
+    from stitch_b200.pipeline import HotPath, make_pair_batch
+    pb = make_pair_batch(3, 3, size=256, iters=3).map(lambda t: t.cuda())
+    a = HotPath(size=256, iters=3, pyramid=True, bidirectional=True).step(pb)
+    sb._lib.reset_launch_count()
+    b_ = HotPath(size=256, iters=3, pyramid=True, bidirectional=False).step(pb)
+    torch.cuda.synchronize()
+    for k in ("cost_volume", "cost_volume_back", "final_warp_output", "overlap", "origin_occlusion_mask"):
+        assert torch.equal(a[k], b_[k]), k
+    assert len(a["cost_tokens"]) == len(b_["cost_tokens"]) == 6
+    for x, y in zip(a["cost_tokens"], b_["cost_tokens"]):
+        assert torch.equal(x, y)
+    for x, y in zip(a["cost_pyramid"] + a["cost_pyramid_back"], b_["cost_pyramid"] + b_["cost_pyramid_back"]):
+        assert torch.equal(x, y)
+
+
 def test_corr_errors(sb):
     with pytest.raises(RuntimeError, match="C=320"):
         sb.corr.corr(torch.zeros(1, 320, 8, 8, device="cuda"), torch.zeros(1, 320, 8, 8, device="cuda"))
@@ -1140,7 +1177,7 @@ def test_hot_path_step_small(sb):
     assert max_abs(host(out["cost_volume"]), vol) <= 1e-2 * float(np.abs(vol).max())
     maps = host(out["cost_volume"]).reshape(-1, 1, 16, 16)
     assert_bits_equal(host(out["cost_tokens"][1].contiguous()),
-                      np.ascontiguousarray(so.encode_flow_token(maps, pb.coords[1].numpy())), "lookup")
+                      np.ascontiguousarray(so.encode_flow_token(maps, pb.coords[1, 0].numpy())), "lookup")
     occ = so.compute_occlusion_wang(pb.flow_ji.numpy(), True, threshold=True)
     assert (host(out["origin_occlusion_mask"]) != occ).mean() < 1e-4
     ref_fw, ref_ov = so.warp(host(out["output_H"]), pb.flow_ij.numpy(), mul_mask=host(out["origin_occlusion_mask"]),
@@ -1188,7 +1225,7 @@ def test_config3_batch64_volume_and_lookup_indexing(sb):
     big = hp.step(pb)
     torch.cuda.synchronize()
     for s0 in (0, 48):
-        part = pb.map(lambda t: t[s0:s0 + 16].contiguous() if t.shape[0] == b else t[:, s0:s0 + 16].contiguous())
+        part = pb.map(lambda t: t[s0:s0 + 16].contiguous() if t.shape[0] == b else t[:, :, s0:s0 + 16].contiguous())
         small = hp.step(part)
         for k in ("final_warp_output", "overlap", "origin_occlusion_mask", "output_H", "cost_volume"):
             assert torch.equal(big[k][s0:s0 + 16], small[k]), (k, s0)

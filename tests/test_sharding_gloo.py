@@ -28,7 +28,7 @@ def test_pair_inputs_independent_of_sharding():
     part = make_pair_batch(2, 2, size=64, iters=1)
     for a, b in zip(whole.tensors()[:7], part.tensors()[:7]):
         assert torch.equal(a[2:4], b)
-    assert torch.equal(whole.coords[:, 2:4], part.coords)
+    assert torch.equal(whole.coords[:, :, 2:4], part.coords)
 
 
 def _worker(rank, world, port, n_pairs, q):

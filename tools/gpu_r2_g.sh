@@ -13,6 +13,7 @@ timeout 600 python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > 
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 timeout 300 python tools/profile_targets.py > gpurun_out/plain2.log 2>&1 && \
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"corr_umma|corr_lookup_r4|flow_warp|homo_warp|range_splat|range_finalize|feat_to_tokens|patch_embed_umma" --profile-from-start off -c 40 -o gpurun_out/prof_r2 -f python tools/profile_targets.py > gpurun_out/ncu_full.log 2>&1
-for f in r2_pytest_gpu r2_kernel_bench r2_bench r2_bench_b64 r2_bench_ref; do echo "== $f"; tail -n 40 gpurun_out/$f.log | cut -c1-600; done
+timeout 600 python tools/config45_bench.py > gpurun_out/r2_configs_4_5.log 2>&1; echo "exit $?" >> gpurun_out/r2_configs_4_5.log
+for f in r2_configs_4_5 r2_pytest_gpu r2_kernel_bench r2_bench r2_bench_b64 r2_bench_ref; do echo "== $f"; tail -n 40 gpurun_out/$f.log | cut -c1-600; done
 tail -n 3 gpurun_out/ncu_full.log
 ls -la gpurun_out/*.ncu-rep

@@ -102,7 +102,10 @@ def test_patch_reference_assigns_call_sites():
         assert ref_gma.Aggregate.forward is stitch_b200.gma.aggregate_forward
         from core.UDIS2.Homography.network import UDIS2Network
         assert UDIS2Network.CCL is stitch_b200.udis2_homography.udis2_network_ccl
-        assert len(done) >= 16
+        from core.FlowFormer.PerCostFormer3.encoder import PatchEmbed
+        assert PatchEmbed.forward is stitch_b200.encoder.patch_embed_forward              # N4
+        assert not any(d.endswith("get_tps_transform") for d in done)                   # stays the reference's binding
+        assert len(done) >= 17
     finally:
         for k in list(sys.modules):
             if k not in saved and (k.startswith("core") or k.startswith("timm") or k.startswith("skimage")):

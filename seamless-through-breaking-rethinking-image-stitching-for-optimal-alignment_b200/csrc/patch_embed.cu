@@ -45,10 +45,20 @@ constexpr int kRow1 = 33, kRow2 = 17, kRow3 = 9;          // OW + 1 of conv1 / c
 constexpr int kMB1 = 9, kMB2 = 3, kMB3 = 1;               // 128-row M blocks per map
 constexpr int kA1Entries = 1220;                           // 1 + 34 * 33 data, reads reach 9*128 - 1 + 66 + 2
 constexpr int kA1Bytes = kA1Entries * 16;                  // 19 520
-constexpr int kCh2 = 308, kCh3 = 92;                       // chunk strides (entries): 1 + 18*17 = 307, 1 + 10*9 = 91
+#ifndef SB_PE_CH2
+#define SB_PE_CH2 308
+#define SB_PE_CH3 92
+#endif
+#ifndef SB_PE_BIAS12
+#define SB_PE_BIAS12 0      // 1: b1 / b2 read once per stage as LDS.128 into registers
+#endif
+#ifndef SB_PE_BIAS3
+#define SB_PE_BIAS3 1       // 1: b3 read as LDS.128 (4 channels per load): measured -2.3 %
+#endif
+constexpr int kCh2 = SB_PE_CH2, kCh3 = SB_PE_CH3;          // chunk strides (entries): >= 1 + 18*17 = 307, 1 + 10*9 = 91
 // (measured, round 2: strides 310 / 93 and 312 / 96 — which make the epilogue's 16-byte stores bank-conflict free —
-//  change nothing, and reading the biases as one LDS.128 batch per stage instead of per element made the kernel
-//  8 % slower (2.52 -> 2.73 ms): the epilogues are not what bounds it)
+//  change nothing; b1 / b2 hoisted into registers once per stage: +7 %; in-loop LDS.128 for b1 / b2: no change;
+//  b3 as LDS.128: -2.3 % and kept.  The SB_PE_* macros select these variants at compile time.)
 constexpr int kA2Bytes = (8 * kCh2 + 112) * 16;            // + tail the last chunk's junk rows read (finite zeros)
 constexpr int kA3Bytes = (16 * kCh3 + 56) * 16;
 // ---- weights per CTA (half of the rows), K-major un-swizzled: [k/8][n/8][n%8][k%8]
@@ -316,6 +326,16 @@ patch_embed_umma_kernel(const Params p) {
         if (t >= 1) ptx::mbar_wait(bar_m2_done + 8 * ((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), 9, p.dbg);   // conv2(t-1) has read A2
         ptx::tc_fence_after_sync();
         const int mb0 = set_a ? 0 : 5, mb1 = set_a ? 5 : kMB1;
+#if SB_PE_BIAS12 == 1
+        float b1[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 v = reinterpret_cast<const float4*>(bias)[c];
+          b1[4 * c] = v.x; b1[4 * c + 1] = v.y; b1[4 * c + 2] = v.z; b1[4 * c + 3] = v.w;
+        }
+#else
+        const float* b1 = bias;
+#endif
         uint32_t r[2][16];
         tmem_ld_x16(lane_t + kD1Col + mb0 * 16, r[0]);
 #pragma unroll 1
@@ -330,11 +350,22 @@ patch_embed_umma_kernel(const Params p) {
           const int oy = m / kRow1, ox = m - oy * kRow1;
           if (oy < 32 && ox < 32) {
             uint32_t w[8];
+#if SB_PE_BIAS12 == 2
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 bv = reinterpret_cast<const float4*>(bias)[c4];
+              const uint32_t x0 = cur == 0 ? r[0][4 * c4] : r[1][4 * c4], x1 = cur == 0 ? r[0][4 * c4 + 1] : r[1][4 * c4 + 1];
+              const uint32_t x2 = cur == 0 ? r[0][4 * c4 + 2] : r[1][4 * c4 + 2], x3 = cur == 0 ? r[0][4 * c4 + 3] : r[1][4 * c4 + 3];
+              w[2 * c4] = pack_bf16(fmaxf(__uint_as_float(x0) + bv.x, 0.0f), fmaxf(__uint_as_float(x1) + bv.y, 0.0f));
+              w[2 * c4 + 1] = pack_bf16(fmaxf(__uint_as_float(x2) + bv.z, 0.0f), fmaxf(__uint_as_float(x3) + bv.w, 0.0f));
+            }
+#else
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const uint32_t x0 = cur == 0 ? r[0][2 * c] : r[1][2 * c], x1 = cur == 0 ? r[0][2 * c + 1] : r[1][2 * c + 1];
-              w[c] = pack_bf16(fmaxf(__uint_as_float(x0) + bias[2 * c], 0.0f), fmaxf(__uint_as_float(x1) + bias[2 * c + 1], 0.0f));
+              w[c] = pack_bf16(fmaxf(__uint_as_float(x0) + b1[2 * c], 0.0f), fmaxf(__uint_as_float(x1) + b1[2 * c + 1], 0.0f));
             }
+#endif
             // s2d channel (py, px, c1) -> chunk (py*2 + px)*2 + c1/8 at entry 1 + (oy/2 + 1) * 17 + ox/2
             const uint32_t chunk = (uint32_t)(((oy & 1) * 2 + (ox & 1)) * 2);
             const uint32_t e = sm + oA2 + (chunk * kCh2 + (uint32_t)(1 + ((oy >> 1) + 1) * kRow2 + (ox >> 1))) * 16u;
@@ -354,6 +385,16 @@ patch_embed_umma_kernel(const Params p) {
           ptx::mbar_wait(bar_m2_done + 8 * buf, (uint32_t)((u >> 1) & 1), 10, p.dbg);
           if (u >= 1) ptx::mbar_wait(bar_m3_done + 8 * ((u - 1) & 1), (uint32_t)(((u - 1) >> 1) & 1), 11, p.dbg);   // conv3(u-1) has read A3
           ptx::tc_fence_after_sync();
+#if SB_PE_BIAS12 == 1
+          float b2[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = reinterpret_cast<const float4*>(bias)[4 + c];
+            b2[4 * c] = v.x; b2[4 * c + 1] = v.y; b2[4 * c + 2] = v.z; b2[4 * c + 3] = v.w;
+          }
+#else
+          const float* b2 = bias + 16;
+#endif
 #pragma unroll 1
           for (int mb = 0; mb < kMB2; ++mb) {
             uint32_t r[32];
@@ -367,10 +408,21 @@ patch_embed_umma_kernel(const Params p) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 uint32_t w[4];
+#if SB_PE_BIAS12 == 2
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                  const float4 bv = reinterpret_cast<const float4*>(bias)[4 + 2 * g + c2];
+                  w[2 * c2] = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 4 * c2]) + bv.x, 0.0f),
+                                        fmaxf(__uint_as_float(r[8 * g + 4 * c2 + 1]) + bv.y, 0.0f));
+                  w[2 * c2 + 1] = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 4 * c2 + 2]) + bv.z, 0.0f),
+                                            fmaxf(__uint_as_float(r[8 * g + 4 * c2 + 3]) + bv.w, 0.0f));
+                }
+#else
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                  w[c] = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 2 * c]) + bias[16 + 8 * g + 2 * c], 0.0f),
-                                   fmaxf(__uint_as_float(r[8 * g + 2 * c + 1]) + bias[16 + 8 * g + 2 * c + 1], 0.0f));
+                  w[c] = pack_bf16(fmaxf(__uint_as_float(r[8 * g + 2 * c]) + b2[8 * g + 2 * c], 0.0f),
+                                   fmaxf(__uint_as_float(r[8 * g + 2 * c + 1]) + b2[8 * g + 2 * c + 1], 0.0f));
+#endif
                 sts128(e + (uint32_t)g * (kCh3 * 16u), w[0], w[1], w[2], w[3]);
               }
             }
@@ -399,9 +451,20 @@ patch_embed_umma_kernel(const Params p) {
             ptx::tmem_ld_32x32b_x32(lane_t + kD3Col + buf * kD3Cols + h * 32, r);
             ptx::tmem_ld_wait();
             if (valid) {
+#if SB_PE_BIAS3
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 bv = reinterpret_cast<const float4*>(bias)[12 + h * 8 + c4];
+                sts32f(st + (uint32_t)(h * 32 + 4 * c4 + 0) * 256u, __uint_as_float(r[4 * c4 + 0]) + bv.x);
+                sts32f(st + (uint32_t)(h * 32 + 4 * c4 + 1) * 256u, __uint_as_float(r[4 * c4 + 1]) + bv.y);
+                sts32f(st + (uint32_t)(h * 32 + 4 * c4 + 2) * 256u, __uint_as_float(r[4 * c4 + 2]) + bv.z);
+                sts32f(st + (uint32_t)(h * 32 + 4 * c4 + 3) * 256u, __uint_as_float(r[4 * c4 + 3]) + bv.w);
+              }
+#else
 #pragma unroll
               for (int c = 0; c < 32; ++c)
                 sts32f(st + (uint32_t)(h * 32 + c) * 256u, __uint_as_float(r[c]) + bias[48 + h * 32 + c]);
+#endif
             }
           }
           ptx::tc_fence_before_sync();

@@ -62,24 +62,37 @@ range_splat_kernel(const float* __restrict__ flow, unsigned long long* __restric
   }
 }
 
+__device__ __forceinline__ float range_finalize_one(unsigned long long a, int mode) {
+  // exact: (double)a is exact below 2^53, the scale is a power of two, one rounding to fp32
+  float v = (float)((double)a * (1.0 / 4294967296.0));
+  if (mode >= 1) {
+    const float c = fminf(fmaxf(v, 0.0f), 1.0f);
+    // compute_occlusion: occ = 1 - clamp(range); occlusion_are_zeros: 1 - occ  (:213-220)
+    const float occ = fsub(1.0f, c);
+    if (mode == 1) v = fsub(1.0f, occ);
+    else if (mode == 2) v = occ;
+    else v = (fsub(1.0f, occ) >= 0.5f) ? 1.0f : 0.0f;
+  }
+  return v;
+}
+
+// Four accumulators per thread (two 16-byte loads, one 16-byte store): the one-element-per-thread version moved 50 MB
+// in 19 us.  `total` need not be a multiple of 4 (tail handled by the last thread's scalar loop).
 __global__ void __launch_bounds__(256)
 range_finalize_kernel(const unsigned long long* __restrict__ accum, float* __restrict__ out,
                       int mode, long long total) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+  const long long nvec = total >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long a = accum[i];
-    // exact hi/lo split keeps 2^-32 resolution below 1.0 and full range above
-    float v = (float)((double)a * (1.0 / 4294967296.0));
-    if (mode >= 1) {
-      const float c = fminf(fmaxf(v, 0.0f), 1.0f);
-      // compute_occlusion: occ = 1 - clamp(range); occlusion_are_zeros: 1 - occ  (:213-220)
-      const float occ = fsub(1.0f, c);
-      if (mode == 1) v = fsub(1.0f, occ);
-      else if (mode == 2) v = occ;
-      else v = (fsub(1.0f, occ) >= 0.5f) ? 1.0f : 0.0f;
-    }
-    out[i] = v;
+    const ulonglong2 a0 = *reinterpret_cast<const ulonglong2*>(accum + 4 * i);
+    const ulonglong2 a1 = *reinterpret_cast<const ulonglong2*>(accum + 4 * i + 2);
+    float4 v;
+    v.x = range_finalize_one(a0.x, mode); v.y = range_finalize_one(a0.y, mode);
+    v.z = range_finalize_one(a1.x, mode); v.w = range_finalize_one(a1.y, mode);
+    *reinterpret_cast<float4*>(out + 4 * i) = v;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = nvec << 2; i < total; ++i) out[i] = range_finalize_one(accum[i], mode);
 }
 
 }  // namespace sb
@@ -97,9 +110,11 @@ extern "C" int sb_range_map(const float* flow, unsigned long long* accum, float*
   SB_REQUIRE(flow && accum && range_map, SB_EINVAL, "sb_range_map: null pointer");
   cudaStream_t s = as_stream(stream);
   SB_CUDA(cudaMemsetAsync(accum, 0, (size_t)total * sizeof(unsigned long long), s));
-  long long blocks = (total + 255) / 256;
+  long long blocks = ((total >> 2) + 255) / 256;            // four elements per thread in the finalise pass
   const long long max_blocks = (long long)kNumSMs * 8 * 16;
   if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  SB_REQUIRE(aligned16(accum) && aligned16(range_map), SB_EINVAL, "sb_range_map: accum and range_map must be 16-byte aligned");
   SB_REQUIRE(B <= 65535 && (H + 7) / 8 <= 65535, SB_EUNSUP, "sb_range_map: B or H too large for one launch");
   range_splat_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, s>>>(flow, accum, H, W);
   SB_LAUNCH_CHECK("range_splat_kernel");

@@ -49,6 +49,12 @@ constexpr int kA1Bytes = kA1Entries * 16;                  // 19 520
 #define SB_PE_CH2 308
 #define SB_PE_CH3 92
 #endif
+#ifndef SB_PE_EXP
+#define SB_PE_EXP 0         // TIMING-ONLY experiments (results are wrong): 1 = 128-byte aligned tap offsets, 2 = no dx != 0 taps,
+#endif                      // 4 = epilogues / loaders do not store to shared memory (tools/pe_variants.sh)
+#ifndef SB_PE_ORDER
+#define SB_PE_ORDER 1       // conv3(t) is issued after conv2(t + 1) has been queued (see the conv3 issuer)
+#endif
 #ifndef SB_PE_BIAS12
 #define SB_PE_BIAS12 0      // 1: b1 / b2 read once per stage as LDS.128 into registers
 #endif
@@ -125,13 +131,17 @@ __device__ __forceinline__ float2 ldg_stream2(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   return v;
 }
+#define SB_PE_STS_GUARD if ((SB_PE_EXP & 4) && addr != 0xFFFFFFF0u) return;
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  SB_PE_STS_GUARD
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  SB_PE_STS_GUARD
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void sts32f(uint32_t addr, float v) {
+  SB_PE_STS_GUARD
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
@@ -169,6 +179,7 @@ patch_embed_umma_kernel(const Params p) {
   const uint32_t bar_e2_done = bar + 88;           // [2] leader: 8 arrivals (D2[i] drained, A3 written)
   const uint32_t bar_e3_done = bar + 104;          // [2] leader: 8 arrivals (D3[i] drained)
   const uint32_t tmem_slot = bar + 128;
+  const uint32_t bar_c2_issued = bar + 136;        // [2] leader, local: the conv2 issuer has queued conv2(t) (orders conv3 behind it)
 
   if (threadIdx.x == 0) {
     ptx::mbar_init(bar_w, 1);
@@ -179,6 +190,7 @@ patch_embed_umma_kernel(const Params p) {
     }
     ptx::mbar_init(bar_d1_full, 1);
     ptx::mbar_init(bar_e1_done, 16);
+    ptx::mbar_init(bar_c2_issued, 1); ptx::mbar_init(bar_c2_issued + 8, 1);
     ptx::fence_mbar_init();
     // this CTA's half of the weights: three bulk copies, one transaction barrier
     ptx::mbar_arrive_expect_tx(bar_w, kWBytes);
@@ -227,7 +239,7 @@ patch_embed_umma_kernel(const Params p) {
           for (int mb = 0; mb < kMB1; ++mb) {
 #pragma unroll
             for (int ks = 0; ks < 3; ++ks)        // ks = dy + 1: input row oy + dy
-              ptx::umma_f16_2cta_elect(d, d64(a_lo + (uint32_t)(kRow1 * ks)), d64(b_lo + (uint32_t)(ks * 16)), idesc(16), ks != 0);
+              ptx::umma_f16_2cta_elect(d, d64(a_lo + (uint32_t)(((SB_PE_EXP & 1) ? 32 : kRow1) * ks)), d64(b_lo + (uint32_t)(ks * 16)), idesc(16), ks != 0);
             a_lo += 128u; d += 16u;
           }
           ptx::umma_commit_2cta_elect(bar_a1_free + 8 * buf, 3);
@@ -246,14 +258,18 @@ patch_embed_umma_kernel(const Params p) {
           for (int mb = 0; mb < kMB2; ++mb) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
+              if ((SB_PE_EXP & 2) && tap % 3 != 1) continue;
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                ptx::umma_f16_2cta_elect(d, d64(a_lo + (uint32_t)(kRow2 * (tap / 3) + (tap % 3) + 2 * j * kCh2)),
+                ptx::umma_f16_2cta_elect(d, d64(a_lo + (uint32_t)(((SB_PE_EXP & 1) ? 16 * (tap / 3) : kRow2 * (tap / 3) + (tap % 3)) + 2 * j * kCh2)),
                                          d64(b_base + (uint32_t)((tap * 8 + 2 * j) * 16)), idesc(32), (tap | j) != 0);
             }
             a_lo += 128u; d += 32u;
           }
           ptx::umma_commit_2cta_elect(bar_m2_done + 8 * buf, 3);
+#if SB_PE_ORDER
+          if (lane == 0) ptx::mbar_arrive(bar_c2_issued + 8 * buf);
+#endif
         }
       } else {
         // ---------------- conv3(t) -> D3[t & 1]: needs A3 written (E2(t)) and that accumulator drained (E3(t-2))
@@ -262,13 +278,21 @@ patch_embed_umma_kernel(const Params p) {
           const int buf = t & 1;
           ptx::mbar_wait(bar_e2_done + 8 * buf, (uint32_t)((t >> 1) & 1), 6, p.dbg);
           if (t >= 2) ptx::mbar_wait(bar_e3_done + 8 * buf, (uint32_t)(((t >> 1) - 1) & 1), 13, p.dbg);
+#if SB_PE_ORDER
+          // Tensor-pipe order.  The pipe executes MMAs in issue order.  E1(t+1) can only start when conv1(t+1) AND
+          // conv2(t) have retired, and while it runs no conv1 / conv2 work exists -- so conv3(t) is queued BEHIND
+          // conv2(t+1)... i.e. behind the conv2 of the next map, and executes during that epilogue instead of competing
+          // with the two layers the epilogue is waiting for (without this the pipe idles for the whole of E1).
+          if (t + 1 < T) ptx::mbar_wait(bar_c2_issued + 8 * ((t + 1) & 1), (uint32_t)(((t + 1) >> 1) & 1), 14, p.dbg);
+#endif
           ptx::tc_fence_after_sync();
           const uint32_t d = tmem_base + kD3Col + buf * kD3Cols;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
+            if ((SB_PE_EXP & 2) && tap % 3 != 1) continue;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              ptx::umma_f16_2cta_elect(d, d64(a_base + (uint32_t)(kRow3 * (tap / 3) + (tap % 3) + 2 * j * kCh3)),
+              ptx::umma_f16_2cta_elect(d, d64(a_base + (uint32_t)(((SB_PE_EXP & 1) ? 8 * (tap / 3) : kRow3 * (tap / 3) + (tap % 3)) + 2 * j * kCh3)),
                                        d64(b_base + (uint32_t)((tap * 16 + 2 * j) * 32)), idesc(64), (tap | j) != 0);
           }
           ptx::umma_commit_2cta_elect(bar_m3_done + 8 * buf, 3);

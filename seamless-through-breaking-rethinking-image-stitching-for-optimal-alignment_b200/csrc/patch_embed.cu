@@ -145,6 +145,14 @@ __device__ __forceinline__ void sts32f(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+#ifdef SB_PE_TRACE
+// Debug build only (tools/pe_variants.sh "trace:-DSB_PE_TRACE", tools/pe_trace.py): clock64() of the pipeline events of
+// CTA 0 in iterations 16..23, 16 events each.
+__device__ long long g_pe_trace[8 * 16 + 2 * 148];   // + per CTA: cycles of the whole kernel, of the steady loop
+#define PE_TRACE(ev) do { if (blockIdx.x == 0 && lane == 0 && t >= 16 && t < 24) g_pe_trace[(t - 16) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define PE_TRACE(ev) do { } while (0)
+#endif
 struct Params {
   const float* maps;        // [NQ, 64, 64] fp32 (cost_maps [NQ, 1, 64, 64])
   float* out;               // [NQ, 64, 8, 8] fp32
@@ -160,6 +168,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 patch_embed_umma_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t sm = ptx::smem_u32(smem_raw);
+#ifdef SB_PE_TRACE
+  const long long trace_k0 = clock64();
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
@@ -175,7 +186,7 @@ patch_embed_umma_kernel(const Params p) {
   const uint32_t bar_d1_full = bar + 40;           // both: conv1 accumulators ready
   const uint32_t bar_m2_done = bar + 48;           // [2] both: conv2 into D2[i] retired (D2[i] ready, A2 reusable)
   const uint32_t bar_m3_done = bar + 64;           // [2] both: conv3 into D3[i] retired (D3[i] ready, A3 reusable)
-  const uint32_t bar_e1_done = bar + 80;           // leader: 16 epilogue-warp arrivals (D1 drained, A2 written)
+  const uint32_t bar_e1_done = bar + 80;           // leader: 24 warp arrivals (D1 drained, A2 written)
   const uint32_t bar_e2_done = bar + 88;           // [2] leader: 8 arrivals (D2[i] drained, A3 written)
   const uint32_t bar_e3_done = bar + 104;          // [2] leader: 8 arrivals (D3[i] drained)
   const uint32_t tmem_slot = bar + 128;
@@ -189,7 +200,7 @@ patch_embed_umma_kernel(const Params p) {
       ptx::mbar_init(bar_e2_done + 8 * i, 8);  ptx::mbar_init(bar_e3_done + 8 * i, 8);
     }
     ptx::mbar_init(bar_d1_full, 1);
-    ptx::mbar_init(bar_e1_done, 16);
+    ptx::mbar_init(bar_e1_done, 24);
     ptx::mbar_init(bar_c2_issued, 1); ptx::mbar_init(bar_c2_issued + 8, 1);
     ptx::fence_mbar_init();
     // this CTA's half of the weights: three bulk copies, one transaction barrier
@@ -214,6 +225,74 @@ patch_embed_umma_kernel(const Params p) {
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + oBar + 128);
   const int T = p.iters;
   const float* bias = reinterpret_cast<const float*>(smem_raw + oBias);
+#ifdef SB_PE_TRACE
+  const long long trace_loop0 = clock64();
+#endif
+
+  // ------------------------------------------------------------------ E1: D1 -> bias, ReLU, bf16 -> conv2's flat s2d buffer
+  // Blocks [mb0, mb1) of map t, by the calling warp's TMEM lane quarter.  Three warp sets share the nine blocks
+  // (E1 sits between conv2(t-1) and conv2(t) on the critical path: A2 is single-buffered).
+  const int wq = warp & 3;
+  const uint32_t lane_t = tmem_base + ((uint32_t)(wq * 32) << 16);
+  const uint32_t e1_tgt = ptx::mapa_shared(bar_e1_done, 0);
+  auto e1_blocks = [&](const int t, const int mb0, const int mb1) {
+    ptx::mbar_wait(bar_d1_full, (uint32_t)(t & 1), 8, p.dbg);
+    if (t >= 1) ptx::mbar_wait(bar_m2_done + 8 * ((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), 9, p.dbg);   // conv2(t-1) has read A2
+    ptx::tc_fence_after_sync();
+    if (wq == 0 && mb0 < 6) PE_TRACE(mb0 == 0 ? 6 : 8);
+#if SB_PE_BIAS12 == 1
+    float b1[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 v = reinterpret_cast<const float4*>(bias)[c];
+      b1[4 * c] = v.x; b1[4 * c + 1] = v.y; b1[4 * c + 2] = v.z; b1[4 * c + 3] = v.w;
+    }
+#else
+    const float* b1 = bias;
+#endif
+    uint32_t r[2][16];
+    tmem_ld_x16(lane_t + kD1Col + mb0 * 16, r[0]);
+#pragma unroll 1
+    for (int mb = mb0; mb < mb1; ++mb) {
+      const int cur = (mb - mb0) & 1;
+      ptx::tmem_ld_wait();
+      if (mb + 1 < mb1) {                          // next block's load in flight while this one is converted
+        if (cur == 0) tmem_ld_x16(lane_t + kD1Col + (mb + 1) * 16, r[1]);
+        else tmem_ld_x16(lane_t + kD1Col + (mb + 1) * 16, r[0]);
+      }
+      const int m = mb * 128 + wq * 32 + lane;
+      const int oy = m / kRow1, ox = m - oy * kRow1;
+      if (oy < 32 && ox < 32) {
+        uint32_t w[8];
+#if SB_PE_BIAS12 == 2
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 bv = reinterpret_cast<const float4*>(bias)[c4];
+          const uint32_t x0 = cur == 0 ? r[0][4 * c4] : r[1][4 * c4], x1 = cur == 0 ? r[0][4 * c4 + 1] : r[1][4 * c4 + 1];
+          const uint32_t x2 = cur == 0 ? r[0][4 * c4 + 2] : r[1][4 * c4 + 2], x3 = cur == 0 ? r[0][4 * c4 + 3] : r[1][4 * c4 + 3];
+          w[2 * c4] = pack_bf16(fmaxf(__uint_as_float(x0) + bv.x, 0.0f), fmaxf(__uint_as_float(x1) + bv.y, 0.0f));
+          w[2 * c4 + 1] = pack_bf16(fmaxf(__uint_as_float(x2) + bv.z, 0.0f), fmaxf(__uint_as_float(x3) + bv.w, 0.0f));
+        }
+#else
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t x0 = cur == 0 ? r[0][2 * c] : r[1][2 * c], x1 = cur == 0 ? r[0][2 * c + 1] : r[1][2 * c + 1];
+          w[c] = pack_bf16(fmaxf(__uint_as_float(x0) + b1[2 * c], 0.0f), fmaxf(__uint_as_float(x1) + b1[2 * c + 1], 0.0f));
+        }
+#endif
+        // s2d channel (py, px, c1) -> chunk (py*2 + px)*2 + c1/8 at entry 1 + (oy/2 + 1) * 17 + ox/2
+        const uint32_t chunk = (uint32_t)(((oy & 1) * 2 + (ox & 1)) * 2);
+        const uint32_t e = sm + oA2 + (chunk * kCh2 + (uint32_t)(1 + ((oy >> 1) + 1) * kRow2 + (ox >> 1))) * 16u;
+        sts128(e, w[0], w[1], w[2], w[3]);
+        sts128(e + kCh2 * 16u, w[4], w[5], w[6], w[7]);
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive_cluster(e1_tgt);
+    if (wq == 0 && mb0 < 6) PE_TRACE(mb0 == 0 ? 7 : 9);
+  };
 
   if (warp == 0 || warp == 2 || warp == 3) {
     // ================================================================ MMA issuers (leader CTA, one warp each)
@@ -233,6 +312,7 @@ patch_embed_umma_kernel(const Params p) {
           if (t >= 1) ptx::mbar_wait(bar_e1_done, (uint32_t)((t - 1) & 1), 2, p.dbg);
           ptx::mbar_wait(bar_ldr_full + 8 * buf, (uint32_t)((t >> 1) & 1), 3, p.dbg);
           ptx::tc_fence_after_sync();
+          PE_TRACE(0);
           uint32_t a_lo = lo_of(sm + oA1 + buf * kA1Bytes, 32u);      // entries (ox - 1) and (ox + 1): LBO = 2 entries
           uint32_t d = tmem_base + kD1Col;
 #pragma unroll 1
@@ -244,6 +324,7 @@ patch_embed_umma_kernel(const Params p) {
           }
           ptx::umma_commit_2cta_elect(bar_a1_free + 8 * buf, 3);
           ptx::umma_commit_2cta_elect(bar_d1_full, 3);
+          PE_TRACE(1);
         }
       } else if (warp == 2) {
         // ---------------- conv2(t) -> D2[t & 1]: needs A2 written (E1(t)) and that accumulator drained (E2(t-2))
@@ -253,6 +334,7 @@ patch_embed_umma_kernel(const Params p) {
           ptx::mbar_wait(bar_e1_done, (uint32_t)(t & 1), 4, p.dbg);
           if (t >= 2) ptx::mbar_wait(bar_e2_done + 8 * buf, (uint32_t)(((t >> 1) - 1) & 1), 5, p.dbg);
           ptx::tc_fence_after_sync();
+          PE_TRACE(2);
           uint32_t a_lo = a_base, d = tmem_base + kD2Col + buf * kD2Cols;
 #pragma unroll 1
           for (int mb = 0; mb < kMB2; ++mb) {
@@ -267,6 +349,7 @@ patch_embed_umma_kernel(const Params p) {
             a_lo += 128u; d += 32u;
           }
           ptx::umma_commit_2cta_elect(bar_m2_done + 8 * buf, 3);
+          PE_TRACE(3);
 #if SB_PE_ORDER
           if (lane == 0) ptx::mbar_arrive(bar_c2_issued + 8 * buf);
 #endif
@@ -286,6 +369,7 @@ patch_embed_umma_kernel(const Params p) {
           if (t + 1 < T) ptx::mbar_wait(bar_c2_issued + 8 * ((t + 1) & 1), (uint32_t)(((t + 1) >> 1) & 1), 14, p.dbg);
 #endif
           ptx::tc_fence_after_sync();
+          PE_TRACE(4);
           const uint32_t d = tmem_base + kD3Col + buf * kD3Cols;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -296,19 +380,21 @@ patch_embed_umma_kernel(const Params p) {
                                        d64(b_base + (uint32_t)((tap * 16 + 2 * j) * 32)), idesc(64), (tap | j) != 0);
           }
           ptx::umma_commit_2cta_elect(bar_m3_done + 8 * buf, 3);
+          PE_TRACE(5);
         }
       }
     }
     __syncwarp();
   } else if (warp >= 12) {
-    // ================================================================ loaders: fp32 map -> bf16 s2d pair entries
+    // ================================================================ loaders: fp32 map -> bf16 s2d pair entries,
+    // and the third E1 set.  Map t + 1 is written to A1 and map t + 2 is on its way in registers before the warp
+    // turns to E1(t), so conv1 never waits for its input.
     const int tid = threadIdx.x - 384;               // 0..127
     const uint32_t full_tgt0 = ptx::mapa_shared(bar_ldr_full, 0);
-    for (int t = 0; t < T; ++t) {
-      const int buf = t & 1;
+    float2 top[8], bot[8];
+    auto fetch = [&](const int t) {                  // global loads of map t into registers
       const long long q = ((long long)t * p.nclusters + cluster_id) * 2 + rank;
-      float2 top[8], bot[8];
-      if (q < p.nq) {                                // issue the global loads before waiting for the buffer
+      if (t < T && q < p.nq) {
         const float* src = p.maps + q * 4096;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {                // s2d position (r, i) = (pos >> 5, pos & 31), pos = tid + 128 j
@@ -317,7 +403,13 @@ patch_embed_umma_kernel(const Params p) {
           bot[j] = ldg_stream2(src + (2 * r + 1) * 64 + 2 * i);
         }
       }
-      if (t >= 2) ptx::mbar_wait(bar_a1_free + 8 * buf, (uint32_t)(((t >> 1) - 1) & 1), 7, p.dbg);
+    };
+    auto publish = [&](const int t) {                // registers -> A1[t & 1], then tell the conv1 issuer
+      if (t >= T) return;
+      const int buf = t & 1;
+      const long long q = ((long long)t * p.nclusters + cluster_id) * 2 + rank;
+      if (t >= 2) ptx::mbar_wait(bar_a1_free + 8 * buf, (uint32_t)(((t >> 1) - 1) & 1), 7, p.dbg);   // conv1(t-2) has read it
+      if (warp == 12) PE_TRACE(14);
       if (q < p.nq) {
         const uint32_t a1 = sm + oA1 + buf * kA1Bytes;
 #pragma unroll
@@ -332,76 +424,24 @@ patch_embed_umma_kernel(const Params p) {
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(full_tgt0 + 8 * buf);
+      if (warp == 12) PE_TRACE(15);
+    };
+    fetch(0); publish(0); fetch(1);
+    for (int t = 0; t < T; ++t) {
+      publish(t + 1);
+      fetch(t + 2);
+      e1_blocks(t, 6, kMB1);
     }
   } else if (warp >= 4) {
-    // ================================================================ epilogues: two warp sets (TMEM lane quarter = warp % 4)
-    //   set A (warps 4-7):  E1 blocks 0..4 of map t, then E3 of map t-2 (+ the output store)
-    //   set B (warps 8-11): E1 blocks 5..8 of map t, then E2 of map t-1
-    const int wq = warp & 3;
+    // ================================================================ epilogues (TMEM lane quarter = warp % 4)
+    //   set A (warps 4-7):  E1 blocks 0..2 of map t, then E3 of map t-2 (+ the output store)
+    //   set B (warps 8-11): E1 blocks 3..5 of map t, then E2 of map t-1
+    //   (the loader warps 12-15 take E1 blocks 6..8)
     const bool set_a = warp < 8;
-    const uint32_t lane_t = tmem_base + ((uint32_t)(wq * 32) << 16);
-    const uint32_t e1_tgt = ptx::mapa_shared(bar_e1_done, 0), e2_tgt = ptx::mapa_shared(bar_e2_done, 0),
-                   e3_tgt = ptx::mapa_shared(bar_e3_done, 0);
+    const uint32_t e2_tgt = ptx::mapa_shared(bar_e2_done, 0), e3_tgt = ptx::mapa_shared(bar_e3_done, 0);
     const int etid = threadIdx.x - 128;               // set A: 0..127
     for (int t = 0; t < T + 2; ++t) {
-      // ---------------- E1(t): D1 -> bias, ReLU, bf16 -> conv2's flat s2d buffer
-      if (t < T) {
-        ptx::mbar_wait(bar_d1_full, (uint32_t)(t & 1), 8, p.dbg);
-        if (t >= 1) ptx::mbar_wait(bar_m2_done + 8 * ((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1), 9, p.dbg);   // conv2(t-1) has read A2
-        ptx::tc_fence_after_sync();
-        const int mb0 = set_a ? 0 : 5, mb1 = set_a ? 5 : kMB1;
-#if SB_PE_BIAS12 == 1
-        float b1[16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 v = reinterpret_cast<const float4*>(bias)[c];
-          b1[4 * c] = v.x; b1[4 * c + 1] = v.y; b1[4 * c + 2] = v.z; b1[4 * c + 3] = v.w;
-        }
-#else
-        const float* b1 = bias;
-#endif
-        uint32_t r[2][16];
-        tmem_ld_x16(lane_t + kD1Col + mb0 * 16, r[0]);
-#pragma unroll 1
-        for (int mb = mb0; mb < mb1; ++mb) {
-          const int cur = (mb - mb0) & 1;
-          ptx::tmem_ld_wait();
-          if (mb + 1 < mb1) {                          // next block's load in flight while this one is converted
-            if (cur == 0) tmem_ld_x16(lane_t + kD1Col + (mb + 1) * 16, r[1]);
-            else tmem_ld_x16(lane_t + kD1Col + (mb + 1) * 16, r[0]);
-          }
-          const int m = mb * 128 + wq * 32 + lane;
-          const int oy = m / kRow1, ox = m - oy * kRow1;
-          if (oy < 32 && ox < 32) {
-            uint32_t w[8];
-#if SB_PE_BIAS12 == 2
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const float4 bv = reinterpret_cast<const float4*>(bias)[c4];
-              const uint32_t x0 = cur == 0 ? r[0][4 * c4] : r[1][4 * c4], x1 = cur == 0 ? r[0][4 * c4 + 1] : r[1][4 * c4 + 1];
-              const uint32_t x2 = cur == 0 ? r[0][4 * c4 + 2] : r[1][4 * c4 + 2], x3 = cur == 0 ? r[0][4 * c4 + 3] : r[1][4 * c4 + 3];
-              w[2 * c4] = pack_bf16(fmaxf(__uint_as_float(x0) + bv.x, 0.0f), fmaxf(__uint_as_float(x1) + bv.y, 0.0f));
-              w[2 * c4 + 1] = pack_bf16(fmaxf(__uint_as_float(x2) + bv.z, 0.0f), fmaxf(__uint_as_float(x3) + bv.w, 0.0f));
-            }
-#else
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint32_t x0 = cur == 0 ? r[0][2 * c] : r[1][2 * c], x1 = cur == 0 ? r[0][2 * c + 1] : r[1][2 * c + 1];
-              w[c] = pack_bf16(fmaxf(__uint_as_float(x0) + b1[2 * c], 0.0f), fmaxf(__uint_as_float(x1) + b1[2 * c + 1], 0.0f));
-            }
-#endif
-            // s2d channel (py, px, c1) -> chunk (py*2 + px)*2 + c1/8 at entry 1 + (oy/2 + 1) * 17 + ox/2
-            const uint32_t chunk = (uint32_t)(((oy & 1) * 2 + (ox & 1)) * 2);
-            const uint32_t e = sm + oA2 + (chunk * kCh2 + (uint32_t)(1 + ((oy >> 1) + 1) * kRow2 + (ox >> 1))) * 16u;
-            sts128(e, w[0], w[1], w[2], w[3]);
-            sts128(e + kCh2 * 16u, w[4], w[5], w[6], w[7]);
-          }
-        }
-        ptx::fence_proxy_async_smem();
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(e1_tgt);
-      }
+      if (t < T) e1_blocks(t, set_a ? 0 : 3, set_a ? 3 : 6);
       if (!set_a) {
         // ---------------- E2(t-1): D2[(t-1) & 1] -> conv3's flat s2d buffer
         if (t >= 1 && t <= T) {
@@ -409,6 +449,7 @@ patch_embed_umma_kernel(const Params p) {
           ptx::mbar_wait(bar_m2_done + 8 * buf, (uint32_t)((u >> 1) & 1), 10, p.dbg);
           if (u >= 1) ptx::mbar_wait(bar_m3_done + 8 * ((u - 1) & 1), (uint32_t)(((u - 1) >> 1) & 1), 11, p.dbg);   // conv3(u-1) has read A3
           ptx::tc_fence_after_sync();
+          if (wq == 0) PE_TRACE(10);
 #if SB_PE_BIAS12 == 1
           float b2[32];
 #pragma unroll
@@ -455,6 +496,7 @@ patch_embed_umma_kernel(const Params p) {
           ptx::tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(e2_tgt + 8 * buf);
+          if (wq == 0) PE_TRACE(11);
         }
       } else {
         // ---------------- E3(t-2): D3[(t-2) & 1] + bias -> fp32 [64, 8, 8] through a staged 16 KB bulk store
@@ -463,6 +505,7 @@ patch_embed_umma_kernel(const Params p) {
           const long long q = ((long long)u * p.nclusters + cluster_id) * 2 + rank;
           ptx::mbar_wait(bar_m3_done + 8 * buf, (uint32_t)((u >> 1) & 1), 12, p.dbg);
           ptx::tc_fence_after_sync();
+          if (wq == 0) PE_TRACE(12);
           if (etid == 0) ptx::tma_store_wait_read<0>();               // the previous map's store has read the staging
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const int m = wq * 32 + lane;
@@ -494,6 +537,7 @@ patch_embed_umma_kernel(const Params p) {
           ptx::tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(e3_tgt + 8 * buf);
+          if (wq == 0) PE_TRACE(13);
           ptx::fence_proxy_async_smem();
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (etid == 0 && q < p.nq) {
@@ -508,6 +552,12 @@ patch_embed_umma_kernel(const Params p) {
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+#ifdef SB_PE_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 148) {
+    g_pe_trace[128 + 2 * blockIdx.x] = clock64() - trace_k0;
+    g_pe_trace[128 + 2 * blockIdx.x + 1] = clock64() - trace_loop0;
+  }
+#endif
   ptx::cluster_sync_all();                            // neither CTA frees TMEM / exits while its peer still uses the pair
   if (warp == 1) {
     ptx::tc_fence_after_sync();
@@ -607,3 +657,11 @@ extern "C" int sb_patch_embed_proj(const float* cost_maps, const void* pack, con
   SB_LAUNCH_CHECK("patch_embed_umma_kernel");
   return SB_OK;
 }
+
+#ifdef SB_PE_TRACE
+// debug builds only (not declared in include/stitch_b200.h): copies the event trace of the last launch to the host
+extern "C" int sb_pe_trace_read(long long* host_out) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  return cudaMemcpyFromSymbol(host_out, sb::pe::g_pe_trace, sizeof(long long) * (8 * 16 + 2 * 148)) == cudaSuccess ? 0 : -1;
+}
+#endif

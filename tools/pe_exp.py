@@ -20,6 +20,28 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); f(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     ts.sort()
+    clk = ""
+    try:                                            # SM clock / power while the kernel runs back to back (~0.7 s)
+        import pynvml, threading, time
+        pynvml.nvmlInit(); hd = pynvml.nvmlDeviceGetHandleByIndex(0)
+        samples, stop = [], threading.Event()
+        def poll():
+            while not stop.is_set():
+                samples.append((pynvml.nvmlDeviceGetClockInfo(hd, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(hd) / 1e3,
+                                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hd)))
+                time.sleep(0.02)
+        th = threading.Thread(target=poll); th.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(300): f()
+        e1.record(); torch.cuda.synchronize(); stop.set(); th.join()
+        sm = sorted(x[0] for x in samples[5:]); pw = sorted(x[1] for x in samples[5:])
+        reasons = 0
+        for x in samples[5:]: reasons |= x[2]
+        clk = "  | 300 back to back: %.1f us each, SM %d MHz median (min %d), %.0f W median (max %.0f), throttle mask 0x%x" % (
+            e0.elapsed_time(e1) / 300 * 1e3, sm[len(sm) // 2], sm[0], pw[len(pw) // 2], pw[-1], reasons)
+    except Exception as ex:
+        clk = "  | clocks unavailable: %r" % (ex,)
     chk = ""
     if len(sys.argv) > 2:
         ref = torch.load(sys.argv[2]) if os.path.exists(sys.argv[2]) else None
@@ -27,7 +49,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
             torch.save(out[:4096].cpu(), sys.argv[2])
         else:
             chk = " identical" if torch.equal(ref, out[:4096].cpu()) else " DIFFERENT (max %.3g)" % (ref - out[:4096].cpu()).abs().max().item()
-    print("%-44s %8.1f us (min of 5, median %.1f)%s" % (os.path.basename(os.environ.get("STITCH_B200_LIB", "default")), ts[0] * 1e3, ts[2] * 1e3, chk), flush=True)
+    print("%-44s %8.1f us (min of 5, median %.1f)%s" % (os.path.basename(os.environ.get("STITCH_B200_LIB", "default")), ts[0] * 1e3, ts[2] * 1e3, chk) + clk, flush=True)
     sys.exit(0)
 libs = [None] + sorted(glob.glob(os.path.join(ROOT, "tools", "probes", "libstitch_pe_*.so")))
 for lib in libs:

@@ -42,7 +42,7 @@ namespace pe {
 constexpr int kThreads = 512;
 // ---- flat activation geometry (entries of 16 bytes)
 constexpr int kRow1 = 33, kRow2 = 17, kRow3 = 9;          // OW + 1 of conv1 / conv2 / conv3
-constexpr int kMB1 = 9, kMB2 = 3, kMB3 = 1;               // 128-row M blocks per map
+constexpr int kMB1 = 8, kMB2 = 2;                         // 128-row M blocks per map (conv3: one, half used)
 constexpr int kA1Entries = 1220;                           // 1 + 34 * 33 data, reads reach 9*128 - 1 + 66 + 2
 constexpr int kA1Bytes = kA1Entries * 16;                  // 19 520
 #ifndef SB_PE_CH2
@@ -149,9 +149,21 @@ __device__ __forceinline__ void sts32f(uint32_t addr, float v) {
 // Debug build only (tools/pe_variants.sh "trace:-DSB_PE_TRACE", tools/pe_trace.py): clock64() of the pipeline events of
 // CTA 0 in iterations 16..23, 16 events each.
 __device__ long long g_pe_trace[8 * 16 + 2 * 148];   // + per CTA: cycles of the whole kernel, of the steady loop
+__device__ long long g_pe_acc[74 * 8];                // per cluster: issuer i (conv1/2/3): [2i] cycles waiting, [2i+1] issuing; [6] smid
 #define PE_TRACE(ev) do { if (blockIdx.x == 0 && lane == 0 && t >= 16 && t < 24) g_pe_trace[(t - 16) * 16 + (ev)] = clock64(); } while (0)
+#define PE_ACC_DECL long long acc_w = 0, acc_i = 0, acc_t = 0
+#define PE_ACC_TOP acc_t = clock64()
+#define PE_ACC_START do { const long long c = clock64(); acc_w += c - acc_t; acc_t = c; } while (0)
+#define PE_ACC_END do { acc_i += clock64() - acc_t; } while (0)
+#define PE_ACC_STORE(i) do { if (lane == 0 && cluster_id < 74) { g_pe_acc[cluster_id * 8 + 2 * (i)] = acc_w; g_pe_acc[cluster_id * 8 + 2 * (i) + 1] = acc_i; \
+    if ((i) == 0) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); g_pe_acc[cluster_id * 8 + 6] = smid; } } } while (0)
 #else
 #define PE_TRACE(ev) do { } while (0)
+#define PE_ACC_DECL do { } while (0)
+#define PE_ACC_TOP do { } while (0)
+#define PE_ACC_START do { } while (0)
+#define PE_ACC_END do { } while (0)
+#define PE_ACC_STORE(i) do { } while (0)
 #endif
 struct Params {
   const float* maps;        // [NQ, 64, 64] fp32 (cost_maps [NQ, 1, 64, 64])
@@ -260,9 +272,9 @@ patch_embed_umma_kernel(const Params p) {
         if (cur == 0) tmem_ld_x16(lane_t + kD1Col + (mb + 1) * 16, r[1]);
         else tmem_ld_x16(lane_t + kD1Col + (mb + 1) * 16, r[0]);
       }
-      const int m = mb * 128 + wq * 32 + lane;
-      const int oy = m / kRow1, ox = m - oy * kRow1;
-      if (oy < 32 && ox < 32) {
+      const int row = wq * 32 + lane;              // core matrix row / 8 = image row of the strip, row % 8 = column
+      const int oy = (mb >> 2) * 16 + (row >> 3), ox = (mb & 3) * 8 + (row & 7);
+      {
         uint32_t w[8];
 #if SB_PE_BIAS12 == 2
 #pragma unroll
@@ -301,64 +313,89 @@ patch_embed_umma_kernel(const Params p) {
     // with the descriptors rebuilt per instruction -> 4.2 ms per 65 536 maps).  Descriptors are a constant high word
     // and a running low word (14-bit address field + LBO): one add per operand and instruction.
     if (leader) {                    // the whole warp runs the loop (converged); one elected lane issues each instruction
-      const uint32_t kHi = (128u >> 4) | (1u << 14);                   // SBO = 128 B, descriptor version 1
+      // Rolled loops (one tap per trip), the election done once per layer, and every descriptor word derived from
+      // warp-uniform values: the issue code of a layer is a few hundred bytes that stay in the instruction cache
+      // (fully unrolled it was 350 B per MMA, 40 KB per iteration streamed from L2 -- and the SMs of a GPC then ran
+      // at visibly different speeds: 3.07 M to 4.0 M cycles for the same 443 maps, tools/pe_trace.py).
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t sm_u = __shfl_sync(0xffffffffu, sm, 0);
+      // High descriptor word = SBO (bytes >> 4) + descriptor version 1.  SBO is the distance between consecutive 8-row
+      // core matrices of the M dimension.  Weights: 128 B (dense).  Activations: ONE ROW of the flat buffer (OW + 1
+      // entries), so that core matrix k is 8 consecutive pixels of image row k: an instruction's 128 rows per CTA are
+      // an 8-pixel-wide, 16-row-high strip of the output and the zero column is never an output row.
       auto lo_of = [](uint32_t addr, uint32_t lbo_bytes) { return ((addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); };
-      auto d64 = [&](uint32_t lo) { return ((uint64_t)kHi << 32) | (uint64_t)lo; };
+      auto d64 = [](uint32_t sbo_entries, uint32_t lo) { return ((uint64_t)(sbo_entries | (1u << 14)) << 32) | (uint64_t)lo; };
       if (warp == 0) {
         // ---------------- conv1(t): needs the entries of map t (loaders) and D1 drained (E1(t-1))
-        const uint32_t b_lo = lo_of(sm + oW1, 128u);
+        const uint32_t b_lo = lo_of(sm_u + oW1, 128u);
+        PE_ACC_DECL;
         for (int t = 0; t < T; ++t) {
           const int buf = t & 1;
+          PE_ACC_TOP;
           if (t >= 1) ptx::mbar_wait(bar_e1_done, (uint32_t)((t - 1) & 1), 2, p.dbg);
           ptx::mbar_wait(bar_ldr_full + 8 * buf, (uint32_t)((t >> 1) & 1), 3, p.dbg);
           ptx::tc_fence_after_sync();
-          PE_TRACE(0);
-          uint32_t a_lo = lo_of(sm + oA1 + buf * kA1Bytes, 32u);      // entries (ox - 1) and (ox + 1): LBO = 2 entries
-          uint32_t d = tmem_base + kD1Col;
+          PE_TRACE(0); PE_ACC_START;
+          uint32_t a_lo = lo_of(sm_u + oA1 + buf * kA1Bytes, 32u);    // entries (ox - 1) and (ox + 1): LBO = 2 entries
+          uint32_t d = tmem_u + kD1Col;
+          const uint32_t el = ptx::elect_one();
 #pragma unroll 1
-          for (int mb = 0; mb < kMB1; ++mb) {
+          for (int mb = 0; mb < kMB1; ++mb) {     // block = rows 16 (mb >> 2) .. + 15, columns 8 (mb & 3) .. + 7
+            const uint32_t a_blk = a_lo + (uint32_t)((mb >> 2) * 16 * kRow1 + (mb & 3) * 8);
 #pragma unroll
             for (int ks = 0; ks < 3; ++ks)        // ks = dy + 1: input row oy + dy
-              ptx::umma_f16_2cta_elect(d, d64(a_lo + (uint32_t)(((SB_PE_EXP & 1) ? 32 : kRow1) * ks)), d64(b_lo + (uint32_t)(ks * 16)), idesc(16), ks != 0);
-            a_lo += 128u; d += 16u;
+              ptx::umma_f16_2cta_if(el, d, d64(kRow1, a_blk + (uint32_t)(kRow1 * ks)), d64(8, b_lo + (uint32_t)(ks * 16)), idesc(16), ks != 0);
+            d += 16u;
           }
           ptx::umma_commit_2cta_elect(bar_a1_free + 8 * buf, 3);
           ptx::umma_commit_2cta_elect(bar_d1_full, 3);
-          PE_TRACE(1);
+          PE_TRACE(1); PE_ACC_END;
         }
+        PE_ACC_STORE(0);
       } else if (warp == 2) {
         // ---------------- conv2(t) -> D2[t & 1]: needs A2 written (E1(t)) and that accumulator drained (E2(t-2))
-        const uint32_t a_base = lo_of(sm + oA2, kCh2 * 16u), b_base = lo_of(sm + oW2, 256u);
+        const uint32_t a_base = lo_of(sm_u + oA2, kCh2 * 16u), b_base = lo_of(sm_u + oW2, 256u);
+        PE_ACC_DECL;
         for (int t = 0; t < T; ++t) {
           const int buf = t & 1;
+          PE_ACC_TOP;
           ptx::mbar_wait(bar_e1_done, (uint32_t)(t & 1), 4, p.dbg);
           if (t >= 2) ptx::mbar_wait(bar_e2_done + 8 * buf, (uint32_t)(((t >> 1) - 1) & 1), 5, p.dbg);
           ptx::tc_fence_after_sync();
-          PE_TRACE(2);
-          uint32_t a_lo = a_base, d = tmem_base + kD2Col + buf * kD2Cols;
+          PE_TRACE(2); PE_ACC_START;
+          uint32_t a_lo = a_base, d = tmem_u + kD2Col + buf * kD2Cols;
+          const uint32_t el = ptx::elect_one();
 #pragma unroll 1
           for (int mb = 0; mb < kMB2; ++mb) {
+            uint32_t b_lo = b_base;
+#pragma unroll 1
+            for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll 1
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint32_t a_tap = a_lo + (uint32_t)(kRow2 * dy + dx);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              if ((SB_PE_EXP & 2) && tap % 3 != 1) continue;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                ptx::umma_f16_2cta_elect(d, d64(a_lo + (uint32_t)(((SB_PE_EXP & 1) ? 16 * (tap / 3) : kRow2 * (tap / 3) + (tap % 3)) + 2 * j * kCh2)),
-                                         d64(b_base + (uint32_t)((tap * 8 + 2 * j) * 16)), idesc(32), (tap | j) != 0);
+                for (int j = 0; j < 4; ++j)
+                  ptx::umma_f16_2cta_if(el, d, d64(kRow2, a_tap + (uint32_t)(2 * j * kCh2)), d64(8, b_lo + (uint32_t)(32 * j)), idesc(32),
+                                        (uint32_t)((dy | dx | j) != 0));
+                b_lo += 128u;
+              }
             }
-            a_lo += 128u; d += 32u;
+            a_lo += 8u; d += 32u;                  // block = all 16 rows, columns 8 mb .. + 7
           }
           ptx::umma_commit_2cta_elect(bar_m2_done + 8 * buf, 3);
-          PE_TRACE(3);
+          PE_TRACE(3); PE_ACC_END;
 #if SB_PE_ORDER
           if (lane == 0) ptx::mbar_arrive(bar_c2_issued + 8 * buf);
 #endif
         }
+        PE_ACC_STORE(1);
       } else {
         // ---------------- conv3(t) -> D3[t & 1]: needs A3 written (E2(t)) and that accumulator drained (E3(t-2))
-        const uint32_t a_base = lo_of(sm + oA3, kCh3 * 16u), b_base = lo_of(sm + oW3, 512u);
+        const uint32_t a_base = lo_of(sm_u + oA3, kCh3 * 16u), b_base = lo_of(sm_u + oW3, 512u);
+        PE_ACC_DECL;
         for (int t = 0; t < T; ++t) {
           const int buf = t & 1;
+          PE_ACC_TOP;
           ptx::mbar_wait(bar_e2_done + 8 * buf, (uint32_t)((t >> 1) & 1), 6, p.dbg);
           if (t >= 2) ptx::mbar_wait(bar_e3_done + 8 * buf, (uint32_t)(((t >> 1) - 1) & 1), 13, p.dbg);
 #if SB_PE_ORDER
@@ -369,19 +406,26 @@ patch_embed_umma_kernel(const Params p) {
           if (t + 1 < T) ptx::mbar_wait(bar_c2_issued + 8 * ((t + 1) & 1), (uint32_t)(((t + 1) >> 1) & 1), 14, p.dbg);
 #endif
           ptx::tc_fence_after_sync();
-          PE_TRACE(4);
-          const uint32_t d = tmem_base + kD3Col + buf * kD3Cols;
+          PE_TRACE(4); PE_ACC_START;
+          const uint32_t d = tmem_u + kD3Col + buf * kD3Cols;
+          const uint32_t el = ptx::elect_one();
+          uint32_t b_lo = b_base;
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll 1
+            for (int dx = 0; dx < 3; ++dx) {
+              const uint32_t a_tap = a_base + (uint32_t)(kRow3 * dy + dx);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            if ((SB_PE_EXP & 2) && tap % 3 != 1) continue;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              ptx::umma_f16_2cta_elect(d, d64(a_base + (uint32_t)(((SB_PE_EXP & 1) ? 8 * (tap / 3) : kRow3 * (tap / 3) + (tap % 3)) + 2 * j * kCh3)),
-                                       d64(b_base + (uint32_t)((tap * 16 + 2 * j) * 32)), idesc(64), (tap | j) != 0);
+              for (int j = 0; j < 8; ++j)
+                ptx::umma_f16_2cta_if(el, d, d64(kRow3, a_tap + (uint32_t)(2 * j * kCh3)), d64(8, b_lo + (uint32_t)(64 * j)), idesc(64),
+                                      (uint32_t)((dy | dx | j) != 0));
+              b_lo += 512u;
+            }
           }
           ptx::umma_commit_2cta_elect(bar_m3_done + 8 * buf, 3);
-          PE_TRACE(5);
+          PE_TRACE(5); PE_ACC_END;
         }
+        PE_ACC_STORE(2);
       }
     }
     __syncwarp();
@@ -436,12 +480,12 @@ patch_embed_umma_kernel(const Params p) {
     // ================================================================ epilogues (TMEM lane quarter = warp % 4)
     //   set A (warps 4-7):  E1 blocks 0..2 of map t, then E3 of map t-2 (+ the output store)
     //   set B (warps 8-11): E1 blocks 3..5 of map t, then E2 of map t-1
-    //   (the loader warps 12-15 take E1 blocks 6..8)
+    //   (the loader warps 12-15 take E1 blocks 6, 7)
     const bool set_a = warp < 8;
     const uint32_t e2_tgt = ptx::mapa_shared(bar_e2_done, 0), e3_tgt = ptx::mapa_shared(bar_e3_done, 0);
     const int etid = threadIdx.x - 128;               // set A: 0..127
     for (int t = 0; t < T + 2; ++t) {
-      if (t < T) e1_blocks(t, set_a ? 0 : 3, set_a ? 3 : 6);
+      if (t < T) e1_blocks(t, set_a ? 0 : 3, set_a ? 3 : 6);     // (loader warps: blocks 6, 7)
       if (!set_a) {
         // ---------------- E2(t-1): D2[(t-1) & 1] -> conv3's flat s2d buffer
         if (t >= 1 && t <= T) {
@@ -465,9 +509,9 @@ patch_embed_umma_kernel(const Params p) {
             uint32_t r[32];
             ptx::tmem_ld_32x32b_x32(lane_t + kD2Col + buf * kD2Cols + mb * 32, r);
             ptx::tmem_ld_wait();
-            const int m = mb * 128 + wq * 32 + lane;
-            const int oy = m / kRow2, ox = m - oy * kRow2;
-            if (oy < 16 && ox < 16) {
+            const int row = wq * 32 + lane;
+            const int oy = row >> 3, ox = mb * 8 + (row & 7);
+            {
               const uint32_t chunk = (uint32_t)(((oy & 1) * 2 + (ox & 1)) * 4);
               const uint32_t e = sm + oA3 + (chunk * kCh3 + (uint32_t)(1 + ((oy >> 1) + 1) * kRow3 + (ox >> 1))) * 16u;
 #pragma unroll
@@ -508,9 +552,9 @@ patch_embed_umma_kernel(const Params p) {
           if (wq == 0) PE_TRACE(12);
           if (etid == 0) ptx::tma_store_wait_read<0>();               // the previous map's store has read the staging
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          const int m = wq * 32 + lane;
-          const int oy = m / kRow3, ox = m - oy * kRow3;
-          const bool valid = oy < 8 && ox < 8;
+          const int m = wq * 32 + lane;              // rows 0..63 = (oy, ox) row-major; rows 64..127 are not outputs
+          const int oy = m >> 3, ox = m & 7;
+          const bool valid = m < 64;
           const uint32_t st = sm + oStage + (uint32_t)(oy * 8 + ox) * 4u;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -660,6 +704,10 @@ extern "C" int sb_patch_embed_proj(const float* cost_maps, const void* pack, con
 
 #ifdef SB_PE_TRACE
 // debug builds only (not declared in include/stitch_b200.h): copies the event trace of the last launch to the host
+extern "C" int sb_pe_acc_read(long long* host_out) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  return cudaMemcpyFromSymbol(host_out, sb::pe::g_pe_acc, sizeof(long long) * 74 * 8) == cudaSuccess ? 0 : -1;
+}
 extern "C" int sb_pe_trace_read(long long* host_out) {
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;
   return cudaMemcpyFromSymbol(host_out, sb::pe::g_pe_trace, sizeof(long long) * (8 * 16 + 2 * 148)) == cudaSuccess ? 0 : -1;

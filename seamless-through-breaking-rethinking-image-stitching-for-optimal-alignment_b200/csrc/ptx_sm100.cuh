@@ -276,6 +276,27 @@ __device__ __forceinline__ void umma_f16_2cta_elect(uint32_t tmem_d, uint64_t ad
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the election done ONCE by the caller (`elected` = elect_one() of a converged warp) and reused for a whole
+// loop of instructions: one predicate test per MMA instead of an election sequence per MMA.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t is_elected;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(is_elected));
+  return is_elected;
+}
+__device__ __forceinline__ void umma_f16_2cta_if(uint32_t elected, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta_elect(uint32_t bar, uint16_t cta_mask) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

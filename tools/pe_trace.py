@@ -32,3 +32,10 @@ print("per-CTA kernel cycles: min %d median %d max %d;  loop only: min %d median
     min(tot), sorted(tot)[74], max(tot), min(loop), sorted(loop)[74], max(loop)))
 print("loop cycles by CTA: " + " ".join(str(x // 1000) for x in loop))
 print("last launch: %.1f us by CUDA events -> slowest CTA ran at %.0f MHz (clock64 cycles / event time)" % (ms[-1] * 1e3, max(tot) / ms[-1] / 1e3))
+acc = (ctypes.c_longlong * (74 * 8))()
+if hasattr(h, "sb_pe_acc_read") and h.sb_pe_acc_read(acc) == 0:
+    print("per cluster (leader CTA): smid | loop kcycles | conv1 wait/issue | conv2 wait/issue | conv3 wait/issue (kcycles)")
+    rows = sorted(range(74), key=lambda c: loop[2 * c])
+    for c in rows:
+        a = [acc[c * 8 + i] // 1000 for i in range(7)]
+        print("cluster %2d smid %3d loop %5d | c1 %5d %5d | c2 %5d %5d | c3 %5d %5d" % (c, acc[c * 8 + 6], loop[2 * c] // 1000, a[0], a[1], a[2], a[3], a[4], a[5]))

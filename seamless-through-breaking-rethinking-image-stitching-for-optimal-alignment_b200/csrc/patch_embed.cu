@@ -10,27 +10,40 @@
 // space-to-depth (2x2 -> 4 channels) image: ky = 2 dy + py + 2, kx = 2 dx + px + 2 with dy, dx in {-1,0,1},
 // py, px in {0,1}.  Activations live in shared memory as a FLAT stream of 16-byte entries (8 bf16 channels), one
 // array per 8-channel chunk, rows of OW + 1 entries whose last entry is a zero column, with one zero row above and
-// below:  entry(iy, ix) = 1 + (iy + 1) * (OW + 1) + ix.   Output position m = oy * (OW + 1) + ox then reads, for tap
-// (dy, dx), entry  m + (OW + 1) * (1 + dy) + dx + 1 - 1: a CONSTANT offset — the left / right zero padding is the
-// zero column of the previous / same row, the top / bottom padding the zero rows.  So the A operand of an implicit
-// GEMM is the activation buffer itself, un-swizzled K-major (core matrix = 8 consecutive entries x 16 bytes,
-// SBO = 128 B, LBO = the chunk stride): no im2col copy, no per-tap staging.  The junk outputs of the zero column
-// (1 in OW + 1) are computed and dropped.
+// below:  entry(iy, ix) = 1 + (iy + 1) * (OW + 1) + ix.   Output pixel (oy, ox) reads, for tap (dy, dx), the entry
+// (OW + 1) * (1 + dy) + dx + 1 - 1 after its own: a CONSTANT offset — the left / right zero padding is the zero column
+// of the previous / same row, the top / bottom padding the zero rows.  So the A operand of an implicit GEMM is the
+// activation buffer itself, un-swizzled K-major: a core matrix = 8 consecutive entries x 16 bytes = 8 horizontally
+// adjacent pixels, LBO = the chunk stride, and SBO (the distance between consecutive core matrices of M) = ONE IMAGE
+// ROW of the buffer, (OW + 1) * 16 bytes.  The 128 rows a CTA contributes to an instruction are therefore an
+// 8-pixel-wide, 16-row-high strip of the output: the zero column is never an output row, no im2col copy, no per-tap
+// staging.  (First version: SBO = 128 B, M = the flat index including the zero column: 9 / 3 / 1 blocks of 128
+// rows with 1 junk row in OW + 1, 12 % slower.)
 //   conv1 (1 -> 16):  K per tap is only 4, so an entry holds TWO horizontally adjacent space-to-depth pixels
 //                     [s2d(ix), s2d(ix+1)]; a K = 16 step is one dy: entry ox-1 (dx = -1, 0) and entry ox+1 (dx = +1, pad).
-//                     M = 33 * 33 flat outputs -> 9 blocks of 128, N = 16, K = 48.
-//   conv2 (16 -> 32): 64 space-to-depth channels = 8 chunks; M = 17 * 17 -> 3 blocks, N = 32, K = 9 * 64 = 576.
-//   conv3 (32 -> 64): 128 channels = 16 chunks; M = 9 * 9 -> 1 block, N = 64, K = 9 * 128 = 1152.
+//                     M = 32 * 32 outputs -> 8 strips of 16 x 8, N = 16, K = 48.
+//   conv2 (16 -> 32): 64 space-to-depth channels = 8 chunks; M = 16 * 16 -> 2 strips, N = 32, K = 9 * 64 = 576.
+//   conv3 (32 -> 64): 128 channels = 16 chunks; M = 8 * 8 = half a strip (rows 64..127 of the instruction are
+//                     unused), N = 64, K = 9 * 128 = 1152.
 // Each epilogue adds the bias, applies ReLU, rounds to bf16 and scatters straight into the next layer's flat
 // space-to-depth buffer; the last one writes the fp32 [64, 8, 8] result through a staged 16 KB bulk store.
 //
 // Machine mapping.  The bf16 weights (186 KB) do not fit one SM next to the activations, so the kernel runs as
 // clusters of two CTAs with tcgen05.mma.cta_group::2: M = 256 per instruction — each CTA supplies the 128 rows of
 // ITS OWN cost map and HALF of the weight rows (N/2), 93 KB per SM.  Per CTA (16 warps): warps 0 / 2 / 3 = MMA
-// issuers of conv1 / conv2 / conv3 (leader CTA), warp 1 = TMEM allocator, warps 4-7 and 8-11 = two epilogue sets
-// (TMEM lane quarter = warp % 4), warps 12-15 = loaders (fp32 map -> bf16 space-to-depth entries).  The three
-// layers run on three consecutive maps at once (conv1(t), conv2(t-1), conv3(t-2)); the conv2 / conv3 accumulators
-// are double-buffered in tensor memory, so an epilogue only ever serialises with the MMAs that read what it writes.
+// issuers of conv1 / conv2 / conv3 (leader CTA; rolled loops on the uniform datapath, see there), warp 1 = TMEM
+// allocator, warps 4-7 / 8-11 / 12-15 = three epilogue sets (TMEM lane quarter = warp % 4) that share conv1's
+// epilogue; set A also runs conv3's, set B conv2's, set C is the loader (fp32 map -> bf16 space-to-depth entries).
+// The three layers run on three consecutive maps at once (conv1(t), conv2(t-1), conv3(t-2)); the conv2 / conv3
+// accumulators are double-buffered in tensor memory.  The tensor pipe executes MMAs in issue order, so the ORDER of
+// issue is part of the design: conv3(t) is queued behind conv2(t+1) and runs while conv1's epilogue converts map
+// t+2 (see the conv3 issuer).  tools/pe_trace.py prints the pipeline's timeline from a -DSB_PE_TRACE build.
+//
+// Measured dead ends (round 2, all bit-identical, tools/pe_variants.sh): double-buffering A2 at the cost of a single
+// A1 and an unstaged output store (+16 %); all of E1's tcgen05.ld issued up front with conv1 released by a separate
+// "D1 drained" barrier (+3 %), the same with conv3 (or its second half) held back until those loads have landed
+// (+13..45 %: a tcgen05.ld completes only after the MMAs issued before it, but coupling the conv3 issue to the
+// epilogue warps serialises them with E2 / E3), E1 on two dedicated sets with E2 / E3 on the loader warps (+4..25 %).
 #include <cuda_bf16.h>
 
 #include "common.cuh"

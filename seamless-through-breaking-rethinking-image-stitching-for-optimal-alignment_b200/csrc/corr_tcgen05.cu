@@ -94,6 +94,9 @@ constexpr int kPanelBytes = BM * 128;              // 16 KB
 constexpr int kStages = SB_CORR_BSTAGES;
 constexpr int kSBufs = SB_CORR_SBUFS;               // staging buffers per epilogue warp
 constexpr int kTilesPerUnit = 4;
+#ifndef SB_CORR_ROLL_TT
+#define SB_CORR_ROLL_TT 1   // the epilogue's loop over the 4 tiles of a unit is NOT unrolled: 76 -> 46 KB of SASS with the fused
+#endif                      // pyramid (the unrolled body alone exceeded the 32 KB instruction-cache level): 292.8 -> 289.7 us
 constexpr int kAccBufs = 4;                        // 4 x 128 TMEM columns
 constexpr int kTmemCols = 512;
 constexpr int kStageBufBytes = 32 * 128;           // per-warp staging: 32 rows x 32 fp32
@@ -534,7 +537,11 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       // a unit is p.tpu tiles (a multiple of 4 when pooling): the pooling state closes every 4 tiles, the A block stays
       for (int tb = t0; tb < t1; tb += kTilesPerUnit) {
+#if SB_CORR_ROLL_TT
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
       for (int tt = 0; tt < kTilesPerUnit; ++tt) {
         const int t = tb + tt;
         if (t >= t1) break;

@@ -29,6 +29,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#define SB_MBAR_SLOW_NOINLINE 0   // setmaxnreg kernels cannot contain calls (ptxas C7600)
 #include "ptx_sm100.cuh"
 #include "tmap.cuh"
 

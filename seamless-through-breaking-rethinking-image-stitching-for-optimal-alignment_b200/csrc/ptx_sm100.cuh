@@ -45,9 +45,14 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 }
 // Bounded wait: a protocol bug must trap (sticky error, process fails loudly),
 // never hang the GPU. `tag` lands in *dbg for post-mortem.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag,
-                                          unsigned int* dbg) {
-  if (mbar_try_wait(bar, parity)) return;
+#ifndef SB_MBAR_SLOW_NOINLINE
+#define SB_MBAR_SLOW_NOINLINE 0   // 1: the spin / timeout path is ONE out-of-line function instead of ~25 instructions inlined at
+#endif                            // every wait site (half of the cost-volume kernel's SASS was this header's inlined helpers)
+#if SB_MBAR_SLOW_NOINLINE
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int tag, unsigned int* dbg) {
+#else
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int tag, unsigned int* dbg) {
+#endif
   const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
     if (globaltimer_ns() - t0 > 2000000000ull) {  // 2 s
@@ -56,6 +61,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag,
+                                          unsigned int* dbg) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, tag, dbg);
 }
 
 // ----------------------------------------------------------------------- TMA

@@ -51,7 +51,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
             chk = " identical" if torch.equal(ref, out[:4096].cpu()) else " DIFFERENT (max %.3g)" % (ref - out[:4096].cpu()).abs().max().item()
     print("%-44s %8.1f us (min of 5, median %.1f)%s" % (os.path.basename(os.environ.get("STITCH_B200_LIB", "default")), ts[0] * 1e3, ts[2] * 1e3, chk) + clk, flush=True)
     sys.exit(0)
-libs = [None] + sorted(glob.glob(os.path.join(ROOT, "tools", "probes", "libstitch_pe_*.so")))
+libs = [None] + sorted(glob.glob(os.path.join(ROOT, "tools", "probes", "libstitch_pe_*.so")) + glob.glob(os.path.join(ROOT, "tools", "probes", "libstitch_patch_embed_*.so")))
 for lib in libs:
     env = dict(os.environ)
     if lib:

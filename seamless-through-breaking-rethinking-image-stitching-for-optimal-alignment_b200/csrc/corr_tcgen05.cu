@@ -459,7 +459,11 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         };
         const int r0 = mb * BM + wq * 32;
         float g2[32], g2a[32], g3[16];               // level-2 partial / first row of the unit, level-3 partial
+#if SB_CORR_ROLL_TT
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int pp = 0; pp < 4; ++pp) {             // pair pp = target rows t0 + 2pp, t0 + 2pp + 1
           const int t = t0 + 2 * pp;
           if (t >= t1) break;

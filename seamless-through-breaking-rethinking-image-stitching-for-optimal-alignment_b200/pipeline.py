@@ -244,7 +244,9 @@ class HotPath:
         if (nsb <= 0 or nsb >= b) and self.lookup_streams == 2:
             # The forward and the backward lookup chains are independent (two separate backbone passes in the reference,
             # flowHomoAdpater.py:177-178; within a chain iteration i+1 depends on i through the GRU): they run on two streams, so that the ramp and the tail of every ~23 us
-            # launch are filled by the other chain's CTAs.  Measured: 12.0 k -> 12.9 k pairs/s (step 1.329 -> 1.241 ms).
+            # launch are filled by the other chain's CTAs.  Measured: 12.0 k -> 12.9 k pairs/s (step 1.329 -> 1.236 ms);
+            # splitting further into sub-batch chains loses again (4 streams 12.2 k, 8 streams 11.2 k), and so does putting
+            # the backward cost volume or the second token conversion on the other stream (12.83 k / 12.80 k).
             cur = torch.cuda.current_stream()
             if self._lk2 is None:
                 self._lk2 = torch.cuda.Stream(maps_f.device, priority=cur.priority)

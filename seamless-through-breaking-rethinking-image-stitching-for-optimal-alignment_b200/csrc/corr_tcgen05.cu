@@ -98,6 +98,20 @@ constexpr int kTilesPerUnit = 4;
 #ifndef SB_CORR_ROLL_TT
 #define SB_CORR_ROLL_TT 1   // the epilogue's loop over the 4 tiles of a unit is NOT unrolled: 76 -> 46 KB of SASS with the fused
 #endif                      // pyramid (the unrolled body alone exceeded the 32 KB instruction-cache level): 292.8 -> 289.7 us
+#ifdef SB_CORR_TRACE
+// Debug build only (tools/build_variants.sh corr_tcgen05 "trace:-DSB_CORR_TRACE", tools/corr_trace.py): per CTA, the
+// cycles each role spent in its waits.  [0] MMA issuer: accumulator not drained, [1] B stage not loaded, [2] A block not
+// loaded; [3] epilogue warp 4: accumulator not ready, [4] staging buffer still being read by an earlier store,
+// [5] its whole loop; [6] producer: no free B stage; [7] smid.
+__device__ long long g_corr_acc[148 * 8];
+#define CT_T0 long long ct_t0 = clock64()
+#define CT_ADD(slot) do { const long long ct_c = clock64(); ct_acc[slot] += ct_c - ct_t0; ct_t0 = ct_c; } while (0)
+#define CT_MARK ct_t0 = clock64()
+#else
+#define CT_T0 do { } while (0)
+#define CT_ADD(slot) do { } while (0)
+#define CT_MARK do { } while (0)
+#endif
 constexpr int kAccBufs = 4;                        // 4 x 128 TMEM columns
 constexpr int kTmemCols = 512;
 constexpr int kStageBufBytes = 32 * 128;           // per-warp staging: 32 rows x 32 fp32
@@ -126,6 +140,7 @@ struct CorrParams {
   int tpu;                      // tiles per unit (kTilesPerUnit; 8 for POOL == 2; NT for the softmax statistics pass)
   float* smx;                   // SMX: per-row (max, sum of exp) [B, N1, 2]; written by pass 1, read by pass 2
   int b_rot;                    // the B operand of batch element b is token map (b + b_rot) mod B (0: the same index)
+  int dyn;                      // 1: work units are handed out by the hardware (cluster launch control), grid = n_units
 };
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
@@ -190,6 +205,11 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t bar_t_full = sBar + 80;    // [kAccBufs]
   const uint32_t bar_t_empty = sBar + 112;  // [kAccBufs]
   const uint32_t tmem_slot = sBar + 144;    // u32
+  // dynamic unit scheduling (p.dyn): two response slots of clusterlaunchcontrol.try_cancel, each with a "response has
+  // landed" barrier (transaction bytes) and an "every reader has decoded it" barrier
+  const uint32_t bar_s_full = sBar + 152;   // [2]
+  const uint32_t bar_s_empty = sBar + 168;  // [2]
+  const uint32_t sResp = sBar + 192;        // [2] x 16 B
   // CTA-pair mode loads half-size B tiles: the same 128 KB ring holds twice as many stages
   constexpr int kStages = TWO_CTA ? 2 * sb::kStages : sb::kStages;
   static_assert(kStages <= 4, "barrier map holds 4 B stages");
@@ -202,6 +222,41 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // work is enumerated per cluster in TWO_CTA mode
   const long long unit0 = TWO_CTA ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
   const long long unit_step = TWO_CTA ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  // ---- work units.  Static: unit0, unit0 + unit_step, ...  Dynamic (p.dyn, one CTA per tile only): the grid has one
+  // CTA per unit; a CTA works on its own blockIdx first and then asks the hardware to cancel the launch of a CTA that
+  // has not started and takes that CTA's index (clusterlaunchcontrol.try_cancel) until none is left -- the SMs do not
+  // run this store-bound kernel at the same speed (tools/corr_trace.py: the slowest ten are 12 % behind the median
+  // with the fused pyramid), and with a static split the whole grid waits for them.  The producer thread issues the
+  // request for unit k + 1 while unit k is loaded; the 16-byte response lands in shared memory (slot k & 1) and every
+  // role decodes it for itself.
+  const bool dyn = !TWO_CTA && p.dyn != 0;
+  auto sched_decode = [&](int m, long long& u) -> bool {          // response m -> unit of iteration m + 1
+    ptx::mbar_wait(bar_s_full + 8 * (m & 1), (uint32_t)((m >> 1) & 1), 20, p.dbg);
+    uint32_t x, y, z, valid;
+    asm volatile(
+        "{\n\t.reg .pred p1;\n\t.reg .b128 resp;\n\t"
+        "ld.shared.b128 resp, [%4];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, resp;\n\t"
+        "selp.u32 %3, 1, 0, p1;\n\t"
+        "mov.u32 %0, 0; mov.u32 %1, 0; mov.u32 %2, 0;\n\t"
+        "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, resp;\n\t}"
+        : "=r"(x), "=r"(y), "=r"(z), "=r"(valid)
+        : "r"(sResp + 16u * (uint32_t)(m & 1))
+        : "memory");
+    (void)y; (void)z;
+    u = (long long)x;
+    return valid != 0;
+  };
+  // consumers (MMA issuer thread, epilogue warps): advance to the next unit; false when there is none
+  auto next_unit = [&](long long& u, int& m, bool one_thread) -> bool {
+    if (!dyn) { u += unit_step; return u < p.n_units; }
+    const bool ok = sched_decode(m, u);
+    ptx::fence_proxy_async_smem();                 // the slot is rewritten through the async proxy
+    if (!one_thread) __syncwarp();
+    if (one_thread || lane == 0) ptx::mbar_arrive(bar_s_empty + 8 * (m & 1));
+    ++m;
+    return ok;
+  };
   constexpr int kBRows = TWO_CTA ? BN / 2 : BN;                   // B rows this CTA loads per tile
   constexpr int kNAcc = ATMEM ? 3 : kAccBufs;                     // accumulator buffers in use
   static_assert(!ATMEM || (POOL != 2 && !TWO_CTA && SMX == 0), "ATMEM: one CTA per tile, POOL 0 / 1 only");
@@ -219,6 +274,10 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(bar_b_full + 8 * s, 1);
       ptx::mbar_init(bar_b_empty + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_s_full + 8 * i, 1);
+      ptx::mbar_init(bar_s_empty + 8 * i, 1 + (blockDim.x >> 5) - 4);   // the MMA issuer + every epilogue warp
     }
     for (int a = 0; a < kAccBufs; ++a) {
       ptx::mbar_init(bar_t_full + 8 * a, 1);
@@ -246,11 +305,24 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ================================================================ producer
     if (lane == 0) {
       uint32_t a_par = 0, stage = 0, b_par = 0;
+#ifdef SB_CORR_TRACE
+      long long ct_acc[1] = {0};
+#endif
+      CT_T0;
       // experiment knob (store_policy bit 2): operand loads keep their lines in L2 (evict_last)
       const uint64_t ld_policy = (p.store_policy & 4) ? ptx::l2_policy_evict_last() : 0ull;
       // TWO_CTA: completions of both CTAs' loads are counted on the LEADER's "full" barriers
       const uint32_t a_full_tgt = TWO_CTA ? ptx::mapa_shared(bar_a_full, 0) : bar_a_full;
-      for (long long u = unit0; u < p.n_units; u += unit_step) {
+      int sm_i = 0;                                 // index of the next scheduler response
+      bool more = unit0 < p.n_units;
+      for (long long u = unit0; more;) {
+        if (dyn) {
+          // ask for the unit after this one: slot sm_i & 1 must have been decoded by every reader of response sm_i - 2
+          if (sm_i >= 2) ptx::mbar_wait(bar_s_empty + 8 * (sm_i & 1), (uint32_t)(((sm_i >> 1) - 1) & 1), 21, p.dbg);
+          ptx::mbar_arrive_expect_tx(bar_s_full + 8 * (sm_i & 1), 16);
+          asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                       ::"r"(sResp + 16u * (uint32_t)(sm_i & 1)), "r"(bar_s_full + 8 * (sm_i & 1)) : "memory");
+        }
         const int ng = (int)(u % p.NG);
         const long long r1 = u / p.NG;
         const int mb = (int)(r1 % p.MB) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
@@ -268,7 +340,9 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int t1 = min(t0 + p.tpu, p.NT);
         const int bb = (b + p.b_rot >= p.B) ? b + p.b_rot - p.B : b + p.b_rot;     // batch element of the B operand
         for (int t = t0; t < t1; ++t) {
+          CT_MARK;
           ptx::mbar_wait(bar_b_empty + 8 * stage, b_par ^ 1, 2, p.dbg);
+          CT_ADD(0);
           if (!TWO_CTA) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, b_tx);
           else if (leader) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, 2 * b_tx);
           const uint32_t b_full_tgt = TWO_CTA ? ptx::mapa_shared(bar_b_full + 8 * stage, 0) : bar_b_full + 8 * stage;
@@ -280,18 +354,34 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           if (++stage == kStages) { stage = 0; b_par ^= 1; }
         }
+        if (dyn) { more = sched_decode(sm_i, u); ++sm_i; }
+        else { u += unit_step; more = u < p.n_units; }
       }
+#ifdef SB_CORR_TRACE
+      if (blockIdx.x < 148) {
+        g_corr_acc[blockIdx.x * 8 + 6] = ct_acc[0];
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); g_corr_acc[blockIdx.x * 8 + 7] = smid;
+      }
+#endif
     }
     __syncwarp();
   } else if (warp == 1) {
     // ============================================================== MMA issuer
     if (lane == 0 && leader) {
       uint32_t a_par = 0, stage = 0, b_par = 0, acc = 0, acc_par = 0;
-      for (long long u = unit0; u < p.n_units; u += unit_step) {
+#ifdef SB_CORR_TRACE
+      long long ct_acc[3] = {0, 0, 0};
+#endif
+      CT_T0;
+      int sm_i = 0;
+      bool more = unit0 < p.n_units;
+      for (long long u = unit0; more; more = next_unit(u, sm_i, true)) {
         const int ng = (int)(u % p.NG);
         const int t0 = ng * p.tpu;
         const int t1 = min(t0 + p.tpu, p.NT);
+        CT_MARK;
         ptx::mbar_wait(bar_a_full, a_par, 3, p.dbg);
+        CT_ADD(2);
         a_par ^= 1;
         const uint32_t a_tmem = tmem_base + 3 * BN;      // ATMEM: columns 384..511
         if (ATMEM) {
@@ -305,8 +395,11 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           ptx::umma_commit(bar_a_empty);                 // the A block in shared memory is free once the copies retire
         }
         for (int t = t0; t < t1; ++t) {
+          CT_MARK;
           ptx::mbar_wait(bar_t_empty + 8 * acc, acc_par ^ 1, 4, p.dbg);
+          CT_ADD(0);
           ptx::mbar_wait(bar_b_full + 8 * stage, b_par, 5, p.dbg);
+          CT_ADD(1);
           ptx::tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + acc * BN;
           for (int kp = 0; kp < p.KP; ++kp) {
@@ -334,6 +427,9 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (TWO_CTA) ptx::umma_commit_2cta(bar_a_empty, 3);
         else if (!ATMEM) ptx::umma_commit(bar_a_empty);  // A reusable once the unit's MMAs retire
       }
+#ifdef SB_CORR_TRACE
+      if (blockIdx.x < 148) for (int i = 0; i < 3; ++i) g_corr_acc[blockIdx.x * 8 + i] = ct_acc[i];
+#endif
     }
     __syncwarp();
   }
@@ -359,7 +455,14 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float h2a[16];  // level-2 row of the unit's first tile pair
     float h1a[32];  // level-1 row of the even tile of a pair
     float h3[8];    // level-3 partial sums across the unit
-    for (long long u = unit0; u < p.n_units; u += unit_step) {
+#ifdef SB_CORR_TRACE
+    long long ct_acc[3] = {0, 0, 0};
+    const long long ct_loop0 = clock64();
+#endif
+    CT_T0;
+    int sm_i = 0;
+    bool more = unit0 < p.n_units;
+    for (long long u = unit0; more; more = next_unit(u, sm_i, false)) {
       const int ng = (int)(u % p.NG);
       const long long r1 = u / p.NG;
       const int mb = (int)(r1 % p.MB) * (TWO_CTA ? 2 : 1) + (int)cta_rank;
@@ -550,7 +653,9 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int tt = 0; tt < kTilesPerUnit; ++tt) {
         const int t = tb + tt;
         if (t >= t1) break;
+        CT_MARK;
         ptx::mbar_wait(bar_t_full + 8 * acc, acc_par, 6, p.dbg);
+        CT_ADD(0);
         ptx::tc_fence_after_sync();
         if (BF16OUT) {
 #pragma unroll
@@ -615,8 +720,10 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
           // staging buffer `sbuf` was last read by the store issued two slices ago
+          CT_MARK;
           if (lane == 0) ptx::tma_store_wait_read<kSBufs - 1>();
           __syncwarp();
+          CT_ADD(1);
           const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -729,6 +836,13 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
     if (lane == 0) ptx::tma_store_wait_all<0>();
+#ifdef SB_CORR_TRACE
+    if (warp == 4 && lane == 0 && blockIdx.x < 148) {
+      g_corr_acc[blockIdx.x * 8 + 3] = ct_acc[0];
+      g_corr_acc[blockIdx.x * 8 + 4] = ct_acc[1];
+      g_corr_acc[blockIdx.x * 8 + 5] = clock64() - ct_loop0;
+    }
+#endif
   }
 
   ptx::tc_fence_before_sync();
@@ -963,7 +1077,9 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
   }
 
   const bool a_tmem = a_tmem_req;
-  const int grid = (int)((p.n_units < kNumSMs) ? p.n_units : kNumSMs);
+  // dynamic unit scheduling (cluster launch control): one CTA per unit in the grid, see the kernel
+  p.dyn = (!two_cta && tune_get(SB_TUNE_CORR_DYNAMIC, 1) != 0 && p.n_units > kNumSMs && p.n_units < (1ll << 30)) ? 1 : 0;
+  const int grid = p.dyn ? (int)p.n_units : (int)((p.n_units < kNumSMs) ? p.n_units : kNumSMs);
   static SmemOptIn opt_in;
   int opt_dev;
   if (opt_in.need(kSmemTotal, &opt_dev)) {
@@ -984,7 +1100,8 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     // pass 1: one unit per row block, all NT tiles; pass 2: the usual units
     CorrParams p1 = p;
     p1.tpu = p.NT; p1.NG = 1; p1.n_units = (long long)B * p.MB;
-    const int grid1 = (int)((p1.n_units < kNumSMs) ? p1.n_units : kNumSMs);
+    p1.dyn = (p.dyn && p1.n_units > kNumSMs) ? 1 : 0;
+    const int grid1 = p1.dyn ? (int)p1.n_units : (int)((p1.n_units < kNumSMs) ? p1.n_units : kNumSMs);
     corr_umma_kernel<0, false, false, 1><<<grid1, 384, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p1);
     SB_LAUNCH_CHECK("corr_umma_kernel<softmax statistics>");
     corr_umma_kernel<0, false, false, 2><<<grid, 256, kSmemTotal, s>>>(map_a, map_b, map_v, map_l1, map_l2, p);
@@ -1065,3 +1182,11 @@ extern "C" int sb_corr(const float* fmap1, const float* fmap2, float* vol, float
   if (rc) return rc;
   return sb_corr_tokens(tok1, tok2, vol, lvl1, lvl2, lvl3, B, C, H1, W1, H2, W2, stream);
 }
+
+#ifdef SB_CORR_TRACE
+// debug builds only (not declared in include/stitch_b200.h)
+extern "C" int sb_corr_acc_read(long long* host_out) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  return cudaMemcpyFromSymbol(host_out, sb::g_corr_acc, sizeof(long long) * 148 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -12,6 +12,11 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
     t1, t2 = C.tokens_bf16(f1), C.tokens_bf16(f2)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     line = os.path.basename(os.environ.get("STITCH_B200_LIB", "default"))
+    if "CORR_TUNE" in os.environ:                   # e.g. CORR_TUNE=14:0 (static unit order)
+        from stitch_b200 import _lib
+        k, v = os.environ["CORR_TUNE"].split(":")
+        _lib.load().sb_tune(int(k), int(v))
+        line += " tune " + os.environ["CORR_TUNE"]
     for lv in (0, 3):
         f = lambda: C.corr_from_tokens(t1, t2, 256, (64, 64), (64, 64), pyramid_levels=lv)
         out = f(); torch.cuda.synchronize()
@@ -33,3 +38,6 @@ for lib in [None] + sorted(glob.glob(os.path.join(ROOT, "tools", "probes", "libs
     if lib:
         env["STITCH_B200_LIB"] = lib
     subprocess.run([sys.executable, __file__, "--one"], env=env, timeout=600)
+    if lib is None and "CORR_TUNE_ALSO" in os.environ:      # the default library once more with a tune key, e.g. 14:0
+        env["CORR_TUNE"] = os.environ["CORR_TUNE_ALSO"]
+        subprocess.run([sys.executable, __file__, "--one"], env=env, timeout=600)

@@ -95,6 +95,10 @@ constexpr int kPanelBytes = BM * 128;              // 16 KB
 constexpr int kStages = SB_CORR_BSTAGES;
 constexpr int kSBufs = SB_CORR_SBUFS;               // staging buffers per epilogue warp
 constexpr int kTilesPerUnit = 4;
+#ifndef SB_CORR_FENCE_PAIRS
+#define SB_CORR_FENCE_PAIRS 1   // the volume slices of a tile are staged two at a time behind ONE fence.proxy.async: the fence
+#endif                          // alone was 400 cycles per slice, 35-52 % of the epilogue warps' time (tools/corr_trace.py):
+                                // 213.0 -> 206.8 us without, 264.2 -> 260.1 us with the fused pyramid, bit-identical
 #ifndef SB_CORR_ROLL_TT
 #define SB_CORR_ROLL_TT 1   // the epilogue's loop over the 4 tiles of a unit is NOT unrolled: 76 -> 46 KB of SASS with the fused
 #endif                      // pyramid (the unrolled body alone exceeded the 32 KB instruction-cache level): 292.8 -> 289.7 us
@@ -104,6 +108,7 @@ constexpr int kTilesPerUnit = 4;
 // loaded; [3] epilogue warp 4: accumulator not ready, [4] staging buffer still being read by an earlier store,
 // [5] its whole loop; [6] producer: no free B stage; [7] smid.
 __device__ long long g_corr_acc[148 * 8];
+__device__ long long g_corr_acc2[148 * 4];         // epilogue warp 4, volume slices: [0] tcgen05.ld, [1] pooling + st.shared, [2] fence + store issue
 #define CT_T0 long long ct_t0 = clock64()
 #define CT_ADD(slot) do { const long long ct_c = clock64(); ct_acc[slot] += ct_c - ct_t0; ct_t0 = ct_c; } while (0)
 #define CT_MARK ct_t0 = clock64()
@@ -456,7 +461,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float h1a[32];  // level-1 row of the even tile of a pair
     float h3[8];    // level-3 partial sums across the unit
 #ifdef SB_CORR_TRACE
-    long long ct_acc[3] = {0, 0, 0};
+    long long ct_acc[6] = {0, 0, 0, 0, 0, 0};      // + [3] tcgen05.ld round trips, [4] pooling + st.shared, [5] fence + store issue
     const long long ct_loop0 = clock64();
 #endif
     CT_T0;
@@ -693,8 +698,10 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) {
           uint32_t r[32];
+          CT_MARK;
           ptx::tmem_ld_32x32b_x32(lane_taddr + acc * BN + sl * 32, r);
           ptx::tmem_ld_wait();
+          CT_ADD(3);
           if (SMX == 2) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -720,8 +727,14 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
           // staging buffer `sbuf` was last read by the store issued two slices ago
-          CT_MARK;
+          CT_ADD(4);
+#if SB_CORR_FENCE_PAIRS
+          // slices are staged in pairs and fenced once: the first of a pair may leave the newest store pending, the
+          // second overwrites the buffer that store reads
+          if (lane == 0) { if (sl & 1) ptx::tma_store_wait_read<0>(); else ptx::tma_store_wait_read<kSBufs - 1>(); }
+#else
           if (lane == 0) ptx::tma_store_wait_read<kSBufs - 1>();
+#endif
           __syncwarp();
           CT_ADD(1);
           const uint32_t dst = my_stage + sbuf * kStageBufBytes + lane * 128;
@@ -732,6 +745,20 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                          "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3])
                          : "memory");
           }
+          CT_ADD(4);
+#if SB_CORR_FENCE_PAIRS
+          static_assert(kSBufs == 2, "pairs of slices use the two staging buffers of a warp");
+          if (sl & 1) {
+            ptx::fence_proxy_async_smem();           // one generic -> async proxy fence for the two slices
+            __syncwarp();
+            if (lane == 0) {
+              TMA_STORE_V(&map_v, my_stage + (sbuf ^ 1) * kStageBufBytes, t * BN + (sl - 1) * 32, mb * BM + wq * 32, b);
+              ptx::tma_store_commit();
+              TMA_STORE_V(&map_v, my_stage + sbuf * kStageBufBytes, t * BN + sl * 32, mb * BM + wq * 32, b);
+              ptx::tma_store_commit();
+            }
+          }
+#else
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -739,7 +766,9 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                               mb * BM + wq * 32, b);
             ptx::tma_store_commit();
           }
+#endif
           if (++sbuf == kSBufs) sbuf = 0;
+          CT_ADD(5);
         }
         }
         // accumulator buffer drained
@@ -840,6 +869,9 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 4 && lane == 0 && blockIdx.x < 148) {
       g_corr_acc[blockIdx.x * 8 + 3] = ct_acc[0];
       g_corr_acc[blockIdx.x * 8 + 4] = ct_acc[1];
+      g_corr_acc2[blockIdx.x * 4 + 0] = ct_acc[3];
+      g_corr_acc2[blockIdx.x * 4 + 1] = ct_acc[4];
+      g_corr_acc2[blockIdx.x * 4 + 2] = ct_acc[5];
       g_corr_acc[blockIdx.x * 8 + 5] = clock64() - ct_loop0;
     }
 #endif
@@ -1185,6 +1217,10 @@ extern "C" int sb_corr(const float* fmap1, const float* fmap2, float* vol, float
 
 #ifdef SB_CORR_TRACE
 // debug builds only (not declared in include/stitch_b200.h)
+extern "C" int sb_corr_acc2_read(long long* host_out) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  return cudaMemcpyFromSymbol(host_out, sb::g_corr_acc2, sizeof(long long) * 148 * 4) == cudaSuccess ? 0 : -1;
+}
 extern "C" int sb_corr_acc_read(long long* host_out) {
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;
   return cudaMemcpyFromSymbol(host_out, sb::g_corr_acc, sizeof(long long) * 148 * 8) == cudaSuccess ? 0 : -1;

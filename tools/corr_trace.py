@@ -33,6 +33,11 @@ for lv in (0, 3):
         v = sorted(r[i] for r in rows)
         print("  %-40s median %8d  min %8d  max %8d   (%.0f %% of the loop)" % (n, v[74], v[0], v[-1], 100.0 * v[74] / loop[74]))
     slow = sorted(range(148), key=lambda c: -rows[c][5])[:5]; fast = sorted(range(148), key=lambda c: rows[c][5])[:5]
+    acc2 = (ctypes.c_longlong * (148 * 4))()
+    if hasattr(h, "sb_corr_acc2_read") and h.sb_corr_acc2_read(acc2) == 0:
+        for i, n in enumerate(["EPI: tcgen05.ld round trips (volume slices)", "EPI: pooling + st.shared", "EPI: fence.proxy.async + TMA store issue"]):
+            v = sorted(acc2[c * 4 + i] for c in range(148))
+            print("  %-44s median %8d  (%.0f %% of the loop)" % (n, v[74], 100.0 * v[74] / loop[74]))
     for tag, lst in (("slowest", sorted(range(148), key=lambda c: -rows[c][5])[:8]), ("fastest", sorted(range(148), key=lambda c: rows[c][5])[:4])):
         for c in lst:
             r = rows[c]

@@ -92,8 +92,19 @@ constexpr int kPanelBytes = BM * 128;              // 16 KB
 #ifndef SB_CORR_SBUFS
 #define SB_CORR_SBUFS 2
 #endif
+#ifndef SB_CORR_PPS
+#define SB_CORR_PPS 4
+#endif
 constexpr int kStages = SB_CORR_BSTAGES;
+constexpr int kPPS = SB_CORR_PPS;                   // K panels per B stage (4 = a whole target tile at C = 256)
 constexpr int kSBufs = SB_CORR_SBUFS;               // staging buffers per epilogue warp
+#ifndef SB_CORR_FENCE_GROUP
+#define SB_CORR_FENCE_GROUP 2
+#endif
+constexpr int kFenceGroup = SB_CORR_FENCE_GROUP;    // volume slices staged behind one fence.proxy.async (2 or 4, <= kSBufs)
+static_assert((kFenceGroup == 2 || kFenceGroup == 4) && kFenceGroup <= SB_CORR_SBUFS, "fence group");
+static_assert(kPPS == 1 || kPPS == 2 || kPPS == 4, "panels per stage");
+static_assert(kSBufs == 2 || kSBufs == 4, "staging buffers per warp");
 constexpr int kTilesPerUnit = 4;
 #ifndef SB_CORR_FENCE_PAIRS
 #define SB_CORR_FENCE_PAIRS 1   // the volume slices of a tile are staged two at a time behind ONE fence.proxy.async: the fence
@@ -121,9 +132,9 @@ constexpr int kAccBufs = 4;                        // 4 x 128 TMEM columns
 constexpr int kTmemCols = 512;
 constexpr int kStageBufBytes = 32 * 128;           // per-warp staging: 32 rows x 32 fp32
 constexpr int kSmemA = kMaxPanels * kPanelBytes;                 // 65536
-constexpr int kSmemB = kStages * kMaxPanels * kPanelBytes;       // 131072
+constexpr int kSmemB = kStages * kPPS * kPanelBytes;             // 131072 (2 stages x 4 panels)
 constexpr int kSmemStage = 4 * kSBufs * kStageBufBytes;          // 32768 with 2 buffers per warp
-constexpr int kSmemBar = 256;
+constexpr int kSmemBar = 512;
 // No alignment slack: the dynamic shared-memory array is declared __align__(1024) (SWIZZLE_128B tiles need it) and
 // the kernel traps if the base is not aligned.  224 KB + 256 B leaves room for the 1 KB-per-CTA reservations of two
 // more shared-memory-free CTAs on the SM (233 472 B per SM): the warp-stage kernels co-reside with this one.
@@ -205,8 +216,8 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t sBar = sStage + kSmemStage;
   // barrier map (8 B each)
   const uint32_t bar_a_full = sBar + 0, bar_a_empty = sBar + 8;
-  const uint32_t bar_b_full = sBar + 16;    // [<= 4 stages]
-  const uint32_t bar_b_empty = sBar + 48;   // [<= 4 stages]
+  const uint32_t bar_b_full = sBar + 256;   // [<= 8 stages]
+  const uint32_t bar_b_empty = sBar + 320;  // [<= 8 stages]
   const uint32_t bar_t_full = sBar + 80;    // [kAccBufs]
   const uint32_t bar_t_empty = sBar + 112;  // [kAccBufs]
   const uint32_t tmem_slot = sBar + 144;    // u32
@@ -217,7 +228,7 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t sResp = sBar + 192;        // [2] x 16 B
   // CTA-pair mode loads half-size B tiles: the same 128 KB ring holds twice as many stages
   constexpr int kStages = TWO_CTA ? 2 * sb::kStages : sb::kStages;
-  static_assert(kStages <= 4, "barrier map holds 4 B stages");
+  static_assert(kStages <= 8, "barrier map holds 8 B stages");
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kSmemA + kSmemB + kSmemStage + 144);
 
@@ -301,7 +312,6 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const uint32_t panel_tx = (uint32_t)p.KP * kPanelBytes;                 // A: this CTA's 128 rows
-  const uint32_t b_tx = (uint32_t)p.KP * kBPanelBytes;                    // B: this CTA's share of a tile
 
   if (warp < 4) {
   // warpgroup 0 (one elected lane each for TMA and MMA issue): hand registers to the epilogue warpgroup
@@ -345,19 +355,23 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int t1 = min(t0 + p.tpu, p.NT);
         const int bb = (b + p.b_rot >= p.B) ? b + p.b_rot - p.B : b + p.b_rot;     // batch element of the B operand
         for (int t = t0; t < t1; ++t) {
-          CT_MARK;
-          ptx::mbar_wait(bar_b_empty + 8 * stage, b_par ^ 1, 2, p.dbg);
-          CT_ADD(0);
-          if (!TWO_CTA) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, b_tx);
-          else if (leader) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, 2 * b_tx);
-          const uint32_t b_full_tgt = TWO_CTA ? ptx::mapa_shared(bar_b_full + 8 * stage, 0) : bar_b_full + 8 * stage;
-          for (int kp = 0; kp < p.KP; ++kp) {
-            const uint32_t dstb = sB + (stage * kMaxPanels + kp) * kBPanelBytes;
-            if (TWO_CTA) ptx::tma_load_3d_2cta(dstb, &map_b, b_full_tgt, kp * BKP, t * BN + (int)cta_rank * kBRows, bb);
-            else if (ld_policy) ptx::tma_load_3d_hint(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, bb, ld_policy);
-            else ptx::tma_load_3d(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, bb);
+          for (int h0 = 0; h0 < p.KP; h0 += kPPS) {          // a stage holds kPPS K panels of the tile
+            const int np = min(kPPS, p.KP - h0);
+            CT_MARK;
+            ptx::mbar_wait(bar_b_empty + 8 * stage, b_par ^ 1, 2, p.dbg);
+            CT_ADD(0);
+            const uint32_t tx = (uint32_t)np * kBPanelBytes;
+            if (!TWO_CTA) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, tx);
+            else if (leader) ptx::mbar_arrive_expect_tx(bar_b_full + 8 * stage, 2 * tx);
+            const uint32_t b_full_tgt = TWO_CTA ? ptx::mapa_shared(bar_b_full + 8 * stage, 0) : bar_b_full + 8 * stage;
+            for (int kp = h0; kp < h0 + np; ++kp) {
+              const uint32_t dstb = sB + (stage * kPPS + (kp - h0)) * kBPanelBytes;
+              if (TWO_CTA) ptx::tma_load_3d_2cta(dstb, &map_b, b_full_tgt, kp * BKP, t * BN + (int)cta_rank * kBRows, bb);
+              else if (ld_policy) ptx::tma_load_3d_hint(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, bb, ld_policy);
+              else ptx::tma_load_3d(dstb, &map_b, bar_b_full + 8 * stage, kp * BKP, t * BN, bb);
+            }
+            if (++stage == kStages) { stage = 0; b_par ^= 1; }
           }
-          if (++stage == kStages) { stage = 0; b_par ^= 1; }
         }
         if (dyn) { more = sched_decode(sm_i, u); ++sm_i; }
         else { u += unit_step; more = u < p.n_units; }
@@ -403,30 +417,31 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           CT_MARK;
           ptx::mbar_wait(bar_t_empty + 8 * acc, acc_par ^ 1, 4, p.dbg);
           CT_ADD(0);
-          ptx::mbar_wait(bar_b_full + 8 * stage, b_par, 5, p.dbg);
-          CT_ADD(1);
-          ptx::tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + acc * BN;
-          for (int kp = 0; kp < p.KP; ++kp) {
-            const uint64_t adesc = ptx::umma_desc_k_sw128(sA + kp * kPanelBytes);
-            const uint64_t bdesc =
-                ptx::umma_desc_k_sw128(sB + (stage * kMaxPanels + kp) * kBPanelBytes);
+          for (int h0 = 0; h0 < p.KP; h0 += kPPS) {
+            const int np = min(kPPS, p.KP - h0);
+            CT_MARK;
+            ptx::mbar_wait(bar_b_full + 8 * stage, b_par, 5, p.dbg);
+            CT_ADD(1);
+            ptx::tc_fence_after_sync();
+            for (int kp = h0; kp < h0 + np; ++kp) {
+              const uint64_t adesc = ptx::umma_desc_k_sw128(sA + kp * kPanelBytes);
+              const uint64_t bdesc =
+                  ptx::umma_desc_k_sw128(sB + (stage * kPPS + (kp - h0)) * kBPanelBytes);
 #pragma unroll
-            for (int k = 0; k < BKP / 16; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
-              if (TWO_CTA) ptx::umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc2, (kp | k) != 0);
-              else if (ATMEM) ptx::umma_f16_ts(d_tmem, a_tmem + (uint32_t)(kp * (BKP / 16) + k) * 8u, bdesc + 2 * k, kIdesc, (kp | k) != 0);
-              else ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kp | k) != 0);
+              for (int k = 0; k < BKP / 16; ++k) {
+                // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4)
+                if (TWO_CTA) ptx::umma_f16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc2, (kp | k) != 0);
+                else if (ATMEM) ptx::umma_f16_ts(d_tmem, a_tmem + (uint32_t)(kp * (BKP / 16) + k) * 8u, bdesc + 2 * k, kIdesc, (kp | k) != 0);
+                else ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kp | k) != 0);
+              }
             }
+            if (TWO_CTA) ptx::umma_commit_2cta(bar_b_empty + 8 * stage, 3);   // both CTAs' B stages reusable
+            else ptx::umma_commit(bar_b_empty + 8 * stage);                    // B stage reusable once these MMAs retire
+            if (++stage == kStages) { stage = 0; b_par ^= 1; }
           }
-          if (TWO_CTA) {
-            ptx::umma_commit_2cta(bar_b_empty + 8 * stage, 3);   // both CTAs' B stages reusable
-            ptx::umma_commit_2cta(bar_t_full + 8 * acc, 3);      // both CTAs' accumulators ready
-          } else {
-            ptx::umma_commit(bar_b_empty + 8 * stage);   // B stage reusable once these MMAs retire
-            ptx::umma_commit(bar_t_full + 8 * acc);      // accumulator ready for the epilogue
-          }
-          if (++stage == kStages) { stage = 0; b_par ^= 1; }
+          if (TWO_CTA) ptx::umma_commit_2cta(bar_t_full + 8 * acc, 3);        // both CTAs' accumulators ready
+          else ptx::umma_commit(bar_t_full + 8 * acc);                         // accumulator ready for the epilogue
           if (++acc == kNAcc) { acc = 0; acc_par ^= 1; }
         }
         if (TWO_CTA) ptx::umma_commit_2cta(bar_a_empty, 3);
@@ -729,9 +744,15 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           // staging buffer `sbuf` was last read by the store issued two slices ago
           CT_ADD(4);
 #if SB_CORR_FENCE_PAIRS
-          // slices are staged in pairs and fenced once: the first of a pair may leave the newest store pending, the
-          // second overwrites the buffer that store reads
-          if (lane == 0) { if (sl & 1) ptx::tma_store_wait_read<0>(); else ptx::tma_store_wait_read<kSBufs - 1>(); }
+          // slices are staged in groups of kFenceGroup and fenced once; slice g of a group overwrites the buffer read by
+          // the store issued kSBufs - g stores ago (none of the group's own stores has been issued yet)
+          if (lane == 0) {
+            const int pend = kSBufs - 1 - (sl % kFenceGroup);
+            if (pend >= 3) ptx::tma_store_wait_read<3>();
+            else if (pend == 2) ptx::tma_store_wait_read<2>();
+            else if (pend == 1) ptx::tma_store_wait_read<1>();
+            else ptx::tma_store_wait_read<0>();
+          }
 #else
           if (lane == 0) ptx::tma_store_wait_read<kSBufs - 1>();
 #endif
@@ -747,15 +768,16 @@ corr_umma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           CT_ADD(4);
 #if SB_CORR_FENCE_PAIRS
-          static_assert(kSBufs == 2, "pairs of slices use the two staging buffers of a warp");
-          if (sl & 1) {
-            ptx::fence_proxy_async_smem();           // one generic -> async proxy fence for the two slices
+          if ((sl % kFenceGroup) == kFenceGroup - 1) {
+            ptx::fence_proxy_async_smem();           // one generic -> async proxy fence for the group's slices
             __syncwarp();
             if (lane == 0) {
-              TMA_STORE_V(&map_v, my_stage + (sbuf ^ 1) * kStageBufBytes, t * BN + (sl - 1) * 32, mb * BM + wq * 32, b);
-              ptx::tma_store_commit();
-              TMA_STORE_V(&map_v, my_stage + sbuf * kStageBufBytes, t * BN + sl * 32, mb * BM + wq * 32, b);
-              ptx::tma_store_commit();
+#pragma unroll
+              for (int i = 0; i < kFenceGroup; ++i) {
+                const uint32_t bi = (sbuf + (uint32_t)(kSBufs - (kFenceGroup - 1 - i))) % (uint32_t)kSBufs;
+                TMA_STORE_V(&map_v, my_stage + bi * kStageBufBytes, t * BN + (sl - (kFenceGroup - 1 - i)) * 32, mb * BM + wq * 32, b);
+                ptx::tma_store_commit();
+              }
             }
           }
 #else

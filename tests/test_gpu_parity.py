@@ -93,6 +93,38 @@ def test_corr_cta_pair_mode_is_bit_identical(sb):
         lib.sb_tune(6, 0)
 
 
+def test_corr_dynamic_units_bit_identical(sb):
+    """Work units handed out by the hardware scheduler (clusterlaunchcontrol.try_cancel, the default) vs the static
+    round-robin split (sb_tune 14 = 0): same bits — volume, fused pyramid (64-wide and the 128-wide pair-of-tiles
+    epilogue), the two-pass attention logits — on shapes with more units than SMs."""
+    lib = sb._lib.load()
+    gen = torch.Generator().manual_seed(15)
+    try:
+        for b, hw, lv in ((3, (64, 64), 3), (2, (64, 64), 0), (1, (128, 128), 3), (5, (40, 56), 0)):
+            f1 = torch.randn(b, 256, *hw, generator=gen)
+            f2 = torch.randn(b, 256, *hw, generator=gen)
+            t1, t2 = sb.corr.tokens_bf16(cu(f1)), sb.corr.tokens_bf16(cu(f2))
+            res = []
+            for mode in (0, 1):
+                assert lib.sb_tune(14, mode) == 0
+                res.append(sb.corr.corr_from_tokens(t1, t2, 256, hw, hw, pyramid_levels=lv))
+            if lv:
+                assert torch.equal(res[0][0], res[1][0])
+                for x, y in zip(res[0][1], res[1][1]):
+                    assert torch.equal(x, y)
+            else:
+                assert torch.equal(res[0], res[1])
+        fmap = cu(torch.randn(2, 128, 64, 64, generator=gen))
+        w_qk = cu(torch.randn(256, 128, 1, 1, generator=gen) * 0.05)
+        att = []
+        for mode in (0, 1):
+            assert lib.sb_tune(14, mode) == 0
+            att.append(sb.gma.attention(fmap, w_qk, heads=1))
+        assert torch.equal(att[0], att[1])
+    finally:
+        lib.sb_tune(14, 1)
+
+
 def test_corr_a_operand_from_tensor_memory_is_bit_identical(sb):
     """A block copied to TMEM once per unit (tcgen05.cp) and read by the TS form of tcgen05.mma (opt-in
     through sb_tune): same bits as the shared-memory-operand kernel; ragged shapes, C = 96 (padded K) and 256."""
@@ -261,6 +293,23 @@ def test_step_bidirectional_equals_two_directions(sb):
         assert torch.equal(x, y)
     for x, y in zip(a["cost_pyramid"] + a["cost_pyramid_back"], b_["cost_pyramid"] + b_["cost_pyramid_back"]):
         assert torch.equal(x, y)
+
+
+def test_step_two_lookup_chains_equal_one(sb):
+    """The forward / backward lookup chains on two streams (default) == one chain after the other."""
+    from stitch_b200.pipeline import HotPath, make_pair_batch
+    pb = make_pair_batch(5, 3, size=256, iters=4).map(lambda t: t.cuda())
+    outs = []
+    for n in (1, 2):
+        hp = HotPath(size=256, iters=4, pyramid=True)
+        hp.lookup_streams = n
+        outs.append(hp.step(pb))
+        torch.cuda.synchronize()
+    assert len(outs[0]["cost_tokens"]) == len(outs[1]["cost_tokens"]) == 8
+    for x, y in zip(outs[0]["cost_tokens"], outs[1]["cost_tokens"]):
+        assert torch.equal(x, y)
+    for k in ("cost_volume", "cost_volume_back", "final_warp_output"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
 
 
 def test_corr_errors(sb):

@@ -102,13 +102,48 @@ def encode_flow_token_pyramid(cost_pyramid, coords, r=4):
     side = 2 * r + 1
     nl = len(cost_pyramid)
     out = torch.empty((b, h1, w1, nl * side * side), dtype=torch.float32, device=co.device)
+    levels = []
     for l, cm in enumerate(cost_pyramid):
         cm = _lib.dev_f32(cm, f"cost_pyramid[{l}]")
         if cm.shape[0] != b * h1 * w1 or cm.shape[1] != 1:
             raise ValueError(f"encode_flow_token_pyramid: level {l} has shape {tuple(cm.shape)}")
-        if cm.shape[0]:
+        levels.append(cm)
+    if not out.numel():
+        return out.permute(0, 3, 1, 2)
+    # The levels are independent launches that write disjoint channel slices of `out`: with
+    # STITCH_B200_PYRAMID_LOOKUP_STREAMS = n > 1 level l runs on stream l mod n (0 = the caller's; the others are forked
+    # from it and joined before returning), so that the ramp and the tail of a launch are filled by another level's
+    # CTAs.  Measured at B = 16 (tools/pyramid_lookup_exp.py): one stream 123 us eager / 115 us inside a captured graph,
+    # two 111-116 / 103, four 162 / 104 (eagerly the extra event records cost more than the overlap gives) -> default 2.
+    cur = torch.cuda.current_stream(co.device)
+    aux = _aux_streams(co.device, nl - 1, cur.priority) if _PYR_STREAMS > 1 else []
+    for st in aux:
+        st.wait_stream(cur)                       # fork once: everything enqueued so far precedes every level
+    for l, cm in enumerate(levels):
+        k = l % (len(aux) + 1)
+        st = aux[k - 1] if k > 0 else None
+        if st is None:
             _lookup_into(cm, co, out, r, 1.0 / (1 << l), nl * side * side, l * side * side)
+        else:
+            with torch.cuda.stream(st):
+                _lookup_into(cm, co, out, r, 1.0 / (1 << l), nl * side * side, l * side * side)
+    for st in aux:
+        cur.wait_stream(st)
     return out.permute(0, 3, 1, 2)
+
+
+import os as _os
+
+_PYR_STREAMS = int(_os.environ.get("STITCH_B200_PYRAMID_LOOKUP_STREAMS", "2"))
+_AUX = {}
+
+
+def _aux_streams(device, n, priority):
+    key = (torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device(), priority)
+    lst = _AUX.setdefault(key, [])
+    while len(lst) < min(n, _PYR_STREAMS - 1):
+        lst.append(torch.cuda.Stream(device, priority=priority))
+    return lst[:min(n, _PYR_STREAMS - 1)]
 
 
 def memory_decoder_encode_flow_token(self, cost_maps, coords, r=4):

@@ -76,7 +76,7 @@ enum {
   SB_TUNE_LOOKUP_GENERIC = 11,     /* EXPERIMENT: 1 = r = 4 lookups take the generic window-staging kernel (LDG.128) instead of the TMA-box kernel */
   SB_TUNE_WARP_TILED = 12,         /* flow / homography warps: 1 = shared-memory-staged tiles where the shape allows (bit-identical, measured slower); default 0 = per-pixel gathers */
   SB_TUNE_CORR_TILES_PER_UNIT = 13, /* cost volume: target tiles per work unit (the A block is loaded once per unit): 4 (default), 8 or 16 */
-  SB_TUNE_CORR_DYNAMIC = 14,       /* cost volume / attention logits: 1 (default) = work units handed out by the hardware scheduler (clusterlaunchcontrol.try_cancel, one CTA per unit in the grid), 0 = static round-robin over 148 persistent CTAs */
+  SB_TUNE_CORR_DYNAMIC = 14,       /* cost volume / attention logits: 1 (default) = work units handed out by the hardware scheduler (clusterlaunchcontrol.try_cancel, one CTA per unit in the grid), 2 = static round-robin over 148 persistent CTAs */
   SB_TUNE_COUNT = 16
 };
 int sb_tune(int key, int value);

@@ -1132,7 +1132,7 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
 
   const bool a_tmem = a_tmem_req;
   // dynamic unit scheduling (cluster launch control): one CTA per unit in the grid, see the kernel
-  p.dyn = (!two_cta && tune_get(SB_TUNE_CORR_DYNAMIC, 1) != 0 && p.n_units > kNumSMs && p.n_units < (1ll << 30)) ? 1 : 0;
+  p.dyn = (!two_cta && tune_get(SB_TUNE_CORR_DYNAMIC, 1) == 1 && p.n_units > kNumSMs && p.n_units < (1ll << 30)) ? 1 : 0;
   const int grid = p.dyn ? (int)p.n_units : (int)((p.n_units < kNumSMs) ? p.n_units : kNumSMs);
   static SmemOptIn opt_in;
   int opt_dev;

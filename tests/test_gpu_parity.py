@@ -95,7 +95,7 @@ def test_corr_cta_pair_mode_is_bit_identical(sb):
 
 def test_corr_dynamic_units_bit_identical(sb):
     """Work units handed out by the hardware scheduler (clusterlaunchcontrol.try_cancel, the default) vs the static
-    round-robin split (sb_tune 14 = 0): same bits — volume, fused pyramid (64-wide and the 128-wide pair-of-tiles
+    round-robin split (sb_tune 14 = 2; 0 means "the default"): same bits — volume, fused pyramid (64-wide and the 128-wide pair-of-tiles
     epilogue), the two-pass attention logits — on shapes with more units than SMs."""
     lib = sb._lib.load()
     gen = torch.Generator().manual_seed(15)
@@ -105,7 +105,7 @@ def test_corr_dynamic_units_bit_identical(sb):
             f2 = torch.randn(b, 256, *hw, generator=gen)
             t1, t2 = sb.corr.tokens_bf16(cu(f1)), sb.corr.tokens_bf16(cu(f2))
             res = []
-            for mode in (0, 1):
+            for mode in (2, 1):
                 assert lib.sb_tune(14, mode) == 0
                 res.append(sb.corr.corr_from_tokens(t1, t2, 256, hw, hw, pyramid_levels=lv))
             if lv:
@@ -117,12 +117,12 @@ def test_corr_dynamic_units_bit_identical(sb):
         fmap = cu(torch.randn(2, 128, 64, 64, generator=gen))
         w_qk = cu(torch.randn(256, 128, 1, 1, generator=gen) * 0.05)
         att = []
-        for mode in (0, 1):
+        for mode in (2, 1):
             assert lib.sb_tune(14, mode) == 0
             att.append(sb.gma.attention(fmap, w_qk, heads=1))
         assert torch.equal(att[0], att[1])
     finally:
-        lib.sb_tune(14, 1)
+        lib.sb_tune(14, 0)
 
 
 def test_corr_a_operand_from_tensor_memory_is_bit_identical(sb):

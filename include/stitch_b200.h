@@ -72,7 +72,7 @@ enum {
   SB_TUNE_CORR_STORE_POLICY = 7,   /* cost volume: L2 policy of the output stores: 1 evict_first (default), 2 evict_last, 3 none */
   SB_TUNE_TPS_LOG = 8,             /* TPS basis log(): 0 = lg2.approx * ln2 (default), 1 = libdevice logf */
   SB_TUNE_LOOKUP_PDL = 9,          /* r = 4 lookup launched with programmatic stream serialization (prologue overlaps the previous kernel's tail): 0 off, 1 on */
-  SB_TUNE_CORR_A_TMEM = 10,        /* cost volume: 1 = the A block is copied to tensor memory once per unit and the MMAs read it from there */
+  SB_TUNE_CORR_A_TMEM = 10,        /* cost volume: 1 (default) = the A block is copied to tensor memory once per unit and the MMAs read it from there, 2 = the MMAs read A from shared memory */
   SB_TUNE_LOOKUP_GENERIC = 11,     /* EXPERIMENT: 1 = r = 4 lookups take the generic window-staging kernel (LDG.128) instead of the TMA-box kernel */
   SB_TUNE_WARP_TILED = 12,         /* flow / homography warps: 1 = shared-memory-staged tiles where the shape allows (bit-identical, measured slower); default 0 = per-pixel gathers */
   SB_TUNE_CORR_TILES_PER_UNIT = 13, /* cost volume: target tiles per work unit (the A block is loaded once per unit): 4 (default), 8 or 16 */

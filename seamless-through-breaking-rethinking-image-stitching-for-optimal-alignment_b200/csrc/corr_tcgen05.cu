@@ -1105,7 +1105,7 @@ static int corr_tokens_impl(const void* tok1, const void* tok2, void* vol_any, l
     return SB_ECUDA;
   }
 
-  const bool a_tmem_req = tune_get(SB_TUNE_CORR_A_TMEM, 0) == 1 && !two_cta && !bf16_out && !smx_stats && pool_mode != 2;
+  const bool a_tmem_req = tune_get(SB_TUNE_CORR_A_TMEM, 1) == 1 && !two_cta && !bf16_out && !smx_stats && pool_mode != 2;
   CorrParams p;
   p.B = B; p.N1 = (int)N1; p.N2 = (int)N2; p.KP = Cpad / 64;
   p.MB = (int)((N1 + BM - 1) / BM);

@@ -126,8 +126,9 @@ def test_corr_dynamic_units_bit_identical(sb):
 
 
 def test_corr_a_operand_from_tensor_memory_is_bit_identical(sb):
-    """A block copied to TMEM once per unit (tcgen05.cp) and read by the TS form of tcgen05.mma (opt-in
-    through sb_tune): same bits as the shared-memory-operand kernel; ragged shapes, C = 96 (padded K) and 256."""
+    """A block copied to TMEM once per unit (tcgen05.cp) and read by the TS form of tcgen05.mma (the default;
+    sb_tune 10 = 2 selects shared-memory operands): same bits as the shared-memory-operand kernel; ragged shapes,
+    C = 96 (padded K) and 256."""
     lib = sb._lib.load()
     gen = torch.Generator().manual_seed(15)
     try:
@@ -136,7 +137,7 @@ def test_corr_a_operand_from_tensor_memory_is_bit_identical(sb):
             f2 = torch.randn(b, c, *hw, generator=gen)
             t1, t2 = sb.corr.tokens_bf16(cu(f1)), sb.corr.tokens_bf16(cu(f2))
             res = []
-            for mode in (0, 1):
+            for mode in (2, 1):
                 lib.sb_tune(10, mode)
                 res.append(sb.corr.corr_from_tokens(t1, t2, c, hw, hw, pyramid_levels=lv))
             if lv:

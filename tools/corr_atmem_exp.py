@@ -14,7 +14,7 @@ for ch in (256, 128):
     f1, f2 = torch.randn(B, ch, 64, 64, device="cuda", generator=g), torch.randn(B, ch, 64, 64, device="cuda", generator=g)
     t1, t2 = C.tokens_bf16(f1), C.tokens_bf16(f2)
     ref = {}
-    for mode in (0, 1, 0, 1):
+    for mode in (2, 1, 2, 1):        # 2 = shared-memory A operand, 1 = A copied to tensor memory (default)
         lib.sb_tune(10, mode)
         for lv in (0, 3):
             out = C.corr_from_tokens(t1, t2, ch, (64, 64), (64, 64), pyramid_levels=lv)
